@@ -1,0 +1,556 @@
+// api.cu -- C ABI of libct3_b200.so (see include/ct3_b200.h): weight packing, workspace carving and the
+// launch sequence of one refinement iteration (cotracker3_offline.py:139-216, cotracker.py:483-531).
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ct3_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace ct3;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_opt_gemm = 0;  // 0 tcgen05, 1 SIMT verification
+int g_opt_corr = 0;  // reserved for correlation kernel variants
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return CT3_ECUDA;
+}
+#define CK(call, where)                                  \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return fail_cuda(e__, where); \
+  } while (0)
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// packed-weights layout
+struct Lin {
+  size_t w = 0, b = 0;  // byte offsets: split weights [N, 2*Kpad] bf16 ; bias [N] fp32
+  int N = 0, K = 0, Kpad = 0;
+};
+struct Block {
+  Lin q;    // self-attention blocks: fused q|k|v (N = 1152); cross blocks: to_q (N = 384)
+  Lin kv;   // cross blocks only: to_kv (N = 768)
+  Lin out, fc1, fc2;
+  size_t ctx_g = 0, ctx_b = 0;  // cross blocks: norm_context weight / bias (fp32 [384])
+  bool cross = false;
+};
+struct Layout {
+  Lin corr_fc1, corr_fc2, in_tr;
+  Block time[kDepth], vself[kDepth], p2v[kDepth], v2p[kDepth];
+  size_t heads_w = 0, heads_b = 0, virt = 0, win_f32 = 0;
+  size_t total = 0;
+};
+
+int pad64(int k) { return (k + 63) / 64 * 64; }
+
+void place_lin(Lin& l, int N, int K, size_t& off) {
+  l.N = N;
+  l.K = K;
+  l.Kpad = pad64(K);
+  l.w = off;
+  off = align_up(off + (size_t)N * 2 * l.Kpad * sizeof(__nv_bfloat16));
+  l.b = off;
+  off = align_up(off + (size_t)N * sizeof(float));
+}
+void place_block(Block& b, bool cross, size_t& off) {
+  b.cross = cross;
+  if (cross) {
+    b.ctx_g = off; off = align_up(off + kC * sizeof(float));
+    b.ctx_b = off; off = align_up(off + kC * sizeof(float));
+    place_lin(b.q, kC, kC, off);
+    place_lin(b.kv, 2 * kC, kC, off);
+  } else {
+    place_lin(b.q, 3 * kC, kC, off);
+  }
+  place_lin(b.out, kC, kC, off);
+  place_lin(b.fc1, kMlpHid, kC, off);
+  place_lin(b.fc2, kC, kMlpHid, off);
+}
+const Layout& layout() {
+  static Layout L;
+  static bool init = false;
+  if (!init) {
+    size_t off = 0;
+    place_lin(L.corr_fc1, kCorrHid, kVol, off);
+    place_lin(L.corr_fc2, kCorrOut, kCorrHid, off);
+    place_lin(L.in_tr, kC, kX, off);
+    L.win_f32 = off; off = align_up(off + (size_t)kC * kX * sizeof(float));
+    L.virt = off;    off = align_up(off + (size_t)kV * kC * sizeof(float));
+    L.heads_w = off; off = align_up(off + 4 * kC * sizeof(float));
+    L.heads_b = off; off = align_up(off + 4 * sizeof(float));
+    for (int i = 0; i < kDepth; ++i) {
+      place_block(L.time[i], false, off);
+      place_block(L.vself[i], false, off);
+      place_block(L.p2v[i], true, off);
+      place_block(L.v2p[i], true, off);
+    }
+    L.total = off;
+    init = true;
+  }
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight tensor order expected by ct3_pack_weights
+const std::vector<std::string>& weight_names() {
+  static std::vector<std::string> names;
+  if (names.empty()) {
+    const char* head[] = {"corr_mlp.fc1.weight", "corr_mlp.fc1.bias", "corr_mlp.fc2.weight", "corr_mlp.fc2.bias",
+                          "updateformer.input_transform.weight", "updateformer.input_transform.bias",
+                          "updateformer.virual_tracks", "updateformer.flow_head.weight", "updateformer.flow_head.bias",
+                          "updateformer.vis_conf_head.weight", "updateformer.vis_conf_head.bias"};
+    for (const char* h : head) names.push_back(h);
+    const char* self_t[] = {"attn.to_q.weight", "attn.to_q.bias", "attn.to_kv.weight", "attn.to_kv.bias",
+                            "attn.to_out.weight", "attn.to_out.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                            "mlp.fc2.weight", "mlp.fc2.bias"};
+    const char* cross_t[] = {"norm_context.weight", "norm_context.bias", "cross_attn.to_q.weight",
+                             "cross_attn.to_q.bias", "cross_attn.to_kv.weight", "cross_attn.to_kv.bias",
+                             "cross_attn.to_out.weight", "cross_attn.to_out.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+                             "mlp.fc2.weight", "mlp.fc2.bias"};
+    for (int i = 0; i < kDepth; ++i) {
+      const std::string idx = std::to_string(i) + ".";
+      for (const char* t : self_t) names.push_back("updateformer.time_blocks." + idx + t);
+      for (const char* t : self_t) names.push_back("updateformer.space_virtual_blocks." + idx + t);
+      for (const char* t : cross_t) names.push_back("updateformer.space_point2virtual_blocks." + idx + t);
+      for (const char* t : cross_t) names.push_back("updateformer.space_virtual2point_blocks." + idx + t);
+    }
+  }
+  return names;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+struct Workspace {
+  __nv_bfloat16* vol;     // [N*T*4, 2*2432]
+  __nv_bfloat16* h1;      // [N*T*4, 2*384]
+  __nv_bfloat16* xs;      // [N*T, 2*1152]
+  float* tokens;          // [(N+64)*T, 384]
+  __nv_bfloat16* ln;      // [(N+64)*T, 2*384]
+  __nv_bfloat16* att;     // [(N+64)*T, 2*384]
+  float* qkv;             // [(N+64)*T, 1152]   (also point q [N*T,384] / point kv [N*T,768])
+  float* vqkv;            // [64*T, 1152]       (virtual q / kv / qkv)
+  __nv_bfloat16* hmid;    // [(N+64)*T, 2*1536]
+  float* row_bias;        // [T, 384]
+  size_t total;
+};
+Workspace carve(void* base, int T, int N) {
+  Workspace w;
+  const size_t R = (size_t)(N + kV) * T, Rp = (size_t)N * T, Rv = (size_t)kV * T, Mc = Rp * kL;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* r = p + off; off = align_up(off + bytes, 1024); return r; };
+  w.vol = (__nv_bfloat16*)take(Mc * 2 * kVolPad * 2);
+  w.h1 = (__nv_bfloat16*)take(Mc * 2 * kCorrHid * 2);
+  w.xs = (__nv_bfloat16*)take(Rp * 2 * kXPad * 2);
+  w.tokens = (float*)take(R * kC * 4);
+  w.ln = (__nv_bfloat16*)take(R * 2 * kC * 2);
+  w.att = (__nv_bfloat16*)take(R * 2 * kC * 2);
+  w.qkv = (float*)take(R * 3 * kC * 4);
+  w.vqkv = (float*)take(Rv * 3 * kC * 4);
+  w.hmid = (__nv_bfloat16*)take(R * 2 * kMlpHid * 2);
+  w.row_bias = (float*)take((size_t)T * kC * 4);
+  w.total = off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Runner {
+  const uint8_t* pk;
+  const Layout& L;
+  cudaStream_t s;
+  int impl;
+  const char* gerr = nullptr;
+
+  int gemm(const __nv_bfloat16* x, const Lin& lin, int M, const GemmEpilogue& e) {
+    GemmProblem p;
+    p.x_split = x;
+    p.w_split = reinterpret_cast<const __nv_bfloat16*>(pk + lin.w);
+    p.M = M;
+    p.N = lin.N;
+    p.Kpad = lin.Kpad;
+    p.epi = e;
+    if (!p.epi.bias) p.epi.bias = reinterpret_cast<const float*>(pk + lin.b);
+    if (M == 0) return 0;
+    return gemm_launch(p, impl, num_sms(), s, &gerr);
+  }
+  static GemmEpilogue to_f32(float* out, int ld, bool residual) {
+    GemmEpilogue e;
+    e.out_f32 = out; e.ld_f32 = ld; e.residual = residual ? 1 : 0;
+    return e;
+  }
+  static GemmEpilogue to_split(__nv_bfloat16* out, int ld, int lo_off, int act) {
+    GemmEpilogue e;
+    e.out_split = out; e.ld_split = ld; e.lo_off = lo_off; e.act = act;
+    return e;
+  }
+};
+
+#define RUN(call)                                                                        \
+  do {                                                                                   \
+    int rc__ = (int)(call);                                                              \
+    if (rc__ != 0) {                                                                     \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s (%s)", #call,                        \
+               cudaGetErrorString((cudaError_t)rc__), R.gerr ? R.gerr : "");             \
+      return CT3_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+// x += to_out(attn(...)); x += mlp(LN(x))   for the rows [row0, row0+rows) of the token buffer
+int mlp_half(Runner& R, const Workspace& W, const Block& b, int64_t row0, int rows) {
+  float* x = W.tokens + row0 * kC;
+  __nv_bfloat16* ln = W.ln + row0 * 2 * kC;
+  __nv_bfloat16* hm = W.hmid + row0 * 2 * kMlpHid;
+  RUN(launch_layernorm_split(x, rows, nullptr, nullptr, 1e-6f, ln, R.s));
+  RUN(R.gemm(ln, b.fc1, rows, Runner::to_split(hm, 2 * kMlpHid, kMlpHid, /*tanh*/ 2)));
+  RUN(R.gemm(hm, b.fc2, rows, Runner::to_f32(x, kC, true)));
+  return 0;
+}
+
+// EfficientUpdateFormer body on W.tokens (point rows already hold input_transform output) -- cotracker.py:486-524
+int transformer_body(Runner& R, const Workspace& W, int T, int N) {
+  const Layout& L = R.L;
+  const int Rp = N * T, Rv = kV * T, Rall = Rp + Rv;
+  const float scale = 1.0f / sqrtf((float)kDh);
+  const uint8_t* pk = R.pk;
+  RUN(launch_init_virtual(W.tokens, reinterpret_cast<const float*>(pk + L.virt), T, N, R.s));
+  float* vtok = W.tokens + (int64_t)Rp * kC;
+  __nv_bfloat16* ln_p = W.ln;
+  __nv_bfloat16* ln_v = W.ln + (int64_t)Rp * 2 * kC;
+  __nv_bfloat16* att_p = W.att;
+  __nv_bfloat16* att_v = W.att + (int64_t)Rp * 2 * kC;
+
+  for (int i = 0; i < kDepth; ++i) {
+    {  // ---- time block over every token row (points + virtual): sequence = track (cotracker.py:494-495)
+      const Block& b = L.time[i];
+      RUN(launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
+      RUN(R.gemm(W.ln, b.q, Rall, Runner::to_f32(W.qkv, 3 * kC, false)));
+      AttnParams a{};
+      a.q = W.qkv; a.q_ld = 3 * kC; a.q_col = 0;
+      a.kv = W.qkv; a.kv_ld = 3 * kC; a.k_col = kC; a.v_col = 2 * kC;
+      a.out = W.att; a.out_ld = 2 * kC; a.lo_off = kC;
+      a.num_seq = N + kV; a.Lq = T; a.Lk = T;
+      a.q_seq_stride = T; a.q_tok_stride = 1; a.k_seq_stride = T; a.k_tok_stride = 1;
+      a.scale = scale;
+      RUN(launch_attention(a, R.s));
+      RUN(R.gemm(W.att, b.out, Rall, Runner::to_f32(W.tokens, kC, true)));
+      if (int rc = mlp_half(R, W, b, 0, Rall)) return rc;
+    }
+    {  // ---- virtual <- point cross attention (cotracker.py:510-512): x = virtual, context = points
+      const Block& b = L.v2p[i];
+      RUN(launch_layernorm_split(vtok, Rv, nullptr, nullptr, 1e-6f, ln_v, R.s));
+      RUN(launch_layernorm_split(W.tokens, Rp, reinterpret_cast<const float*>(pk + b.ctx_g),
+                                 reinterpret_cast<const float*>(pk + b.ctx_b), 1e-5f, ln_p, R.s));
+      RUN(R.gemm(ln_v, b.q, Rv, Runner::to_f32(W.vqkv, kC, false)));
+      RUN(R.gemm(ln_p, b.kv, Rp, Runner::to_f32(W.qkv, 2 * kC, false)));
+      AttnParams a{};
+      a.q = W.vqkv; a.q_ld = kC; a.q_col = 0;
+      a.kv = W.qkv; a.kv_ld = 2 * kC; a.k_col = 0; a.v_col = kC;
+      a.out = att_v; a.out_ld = 2 * kC; a.lo_off = kC;
+      a.num_seq = T; a.Lq = kV; a.Lk = N;
+      a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
+      a.scale = scale;
+      RUN(launch_attention(a, R.s));
+      RUN(R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
+      if (int rc = mlp_half(R, W, b, Rp, Rv)) return rc;
+    }
+    {  // ---- virtual self attention (cotracker.py:514): sequence = frame over the 64 virtual tokens
+      const Block& b = L.vself[i];
+      RUN(launch_layernorm_split(vtok, Rv, nullptr, nullptr, 1e-6f, ln_v, R.s));
+      RUN(R.gemm(ln_v, b.q, Rv, Runner::to_f32(W.vqkv, 3 * kC, false)));
+      AttnParams a{};
+      a.q = W.vqkv; a.q_ld = 3 * kC; a.q_col = 0;
+      a.kv = W.vqkv; a.kv_ld = 3 * kC; a.k_col = kC; a.v_col = 2 * kC;
+      a.out = att_v; a.out_ld = 2 * kC; a.lo_off = kC;
+      a.num_seq = T; a.Lq = kV; a.Lk = kV;
+      a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
+      a.scale = scale;
+      RUN(launch_attention(a, R.s));
+      RUN(R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
+      if (int rc = mlp_half(R, W, b, Rp, Rv)) return rc;
+    }
+    {  // ---- point <- virtual cross attention (cotracker.py:515-517): x = points, context = virtual
+      const Block& b = L.p2v[i];
+      RUN(launch_layernorm_split(W.tokens, Rp, nullptr, nullptr, 1e-6f, ln_p, R.s));
+      RUN(launch_layernorm_split(vtok, Rv, reinterpret_cast<const float*>(pk + b.ctx_g),
+                                 reinterpret_cast<const float*>(pk + b.ctx_b), 1e-5f, ln_v, R.s));
+      RUN(R.gemm(ln_p, b.q, Rp, Runner::to_f32(W.qkv, kC, false)));
+      RUN(R.gemm(ln_v, b.kv, Rv, Runner::to_f32(W.vqkv, 2 * kC, false)));
+      AttnParams a{};
+      a.q = W.qkv; a.q_ld = kC; a.q_col = 0;
+      a.kv = W.vqkv; a.kv_ld = 2 * kC; a.k_col = 0; a.v_col = kC;
+      a.out = att_p; a.out_ld = 2 * kC; a.lo_off = kC;
+      a.num_seq = T; a.Lq = N; a.Lk = kV;
+      a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
+      a.scale = scale;
+      RUN(launch_attention(a, R.s));
+      RUN(R.gemm(att_p, b.out, Rp, Runner::to_f32(W.tokens, kC, true)));
+      if (int rc = mlp_half(R, W, b, 0, Rp)) return rc;
+    }
+  }
+  return 0;
+}
+
+int check_TN(int T, int N) {
+  if (T < 1 || N < 1) return fail(CT3_EINVAL, "T and N must be >= 1%s");
+  if ((int64_t)(N + kV) * T * 3 * kC >= (int64_t)1 << 40) return fail(CT3_EINVAL, "problem too large%s");
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int ct3_version(void) { return 100; }
+const char* ct3_last_error(void) { return g_err; }
+
+int ct3_set_option(const char* name, int value) {
+  if (!name) return fail(CT3_EINVAL, "null option name%s");
+  if (!strcmp(name, "gemm")) { if (value < 0 || value > 1) return fail(CT3_EINVAL, "gemm option must be 0 or 1%s"); g_opt_gemm = value; return 0; }
+  if (!strcmp(name, "corr")) { g_opt_corr = value; return 0; }
+  return fail(CT3_EINVAL, "unknown option %s", name);
+}
+int ct3_get_option(const char* name, int* value) {
+  if (!name || !value) return fail(CT3_EINVAL, "null argument%s");
+  if (!strcmp(name, "gemm")) { *value = g_opt_gemm; return 0; }
+  if (!strcmp(name, "corr")) { *value = g_opt_corr; return 0; }
+  return fail(CT3_EINVAL, "unknown option %s", name);
+}
+
+int ct3_num_weight_tensors(void) { return (int)weight_names().size(); }
+const char* ct3_weight_name(int index) {
+  const auto& n = weight_names();
+  if (index < 0 || index >= (int)n.size()) return nullptr;
+  return n[index].c_str();
+}
+
+int ct3_packed_weights_bytes(size_t* out_bytes) {
+  if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
+  *out_bytes = layout().total;
+  return 0;
+}
+
+int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t packed_bytes, ct3_stream_t stream) {
+  const Layout& L = layout();
+  if (!t || !packed) return fail(CT3_EINVAL, "null argument%s");
+  if (n_tensors != (int)weight_names().size()) return fail(CT3_EINVAL, "wrong number of weight tensors%s");
+  if (packed_bytes < L.total) return fail(CT3_ENOSPC, "packed buffer too small%s");
+  for (int i = 0; i < n_tensors; ++i)
+    if (!t[i]) return fail(CT3_EINVAL, "null weight tensor: %s", weight_names()[i].c_str());
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
+  CK(cudaMemsetAsync(pk, 0, L.total, s), "memset packed");
+  auto put_lin = [&](const Lin& l, const float* w, const float* b, int rows, int row_off, int perm) -> cudaError_t {
+    cudaError_t e = launch_split_rows(w, rows, l.K, l.Kpad, perm, reinterpret_cast<__nv_bfloat16*>(pk + l.w), row_off, s);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(pk + l.b + (size_t)row_off * 4, b, (size_t)rows * 4, cudaMemcpyDeviceToDevice, s);
+  };
+  auto put_f32 = [&](size_t off, const float* src, size_t count) {
+    return cudaMemcpyAsync(pk + off, src, count * 4, cudaMemcpyDeviceToDevice, s);
+  };
+  int k = 0;
+  CK(put_lin(L.corr_fc1, t[k], t[k + 1], kCorrHid, 0, 0), "pack corr_fc1"); k += 2;
+  CK(put_lin(L.corr_fc2, t[k], t[k + 1], kCorrOut, 0, 0), "pack corr_fc2"); k += 2;
+  CK(put_lin(L.in_tr, t[k], t[k + 1], kC, 0, /*perm_x*/ 1), "pack input_transform");
+  CK(put_f32(L.win_f32, t[k], (size_t)kC * kX), "pack input_transform fp32"); k += 2;
+  CK(put_f32(L.virt, t[k], (size_t)kV * kC), "pack virtual tracks"); k += 1;
+  CK(put_f32(L.heads_w, t[k], 2 * kC), "pack flow_head.w");
+  CK(put_f32(L.heads_b, t[k + 1], 2), "pack flow_head.b"); k += 2;
+  CK(put_f32(L.heads_w + 2 * kC * 4, t[k], 2 * kC), "pack vis_conf_head.w");
+  CK(put_f32(L.heads_b + 2 * 4, t[k + 1], 2), "pack vis_conf_head.b"); k += 2;
+  auto put_self = [&](const Block& b) -> cudaError_t {
+    cudaError_t e;
+    if ((e = put_lin(b.q, t[k], t[k + 1], kC, 0, 0)) != cudaSuccess) return e;            // to_q  -> rows [0,384)
+    if ((e = put_lin(b.q, t[k + 2], t[k + 3], 2 * kC, kC, 0)) != cudaSuccess) return e;   // to_kv -> rows [384,1152)
+    if ((e = put_lin(b.out, t[k + 4], t[k + 5], kC, 0, 0)) != cudaSuccess) return e;
+    if ((e = put_lin(b.fc1, t[k + 6], t[k + 7], kMlpHid, 0, 0)) != cudaSuccess) return e;
+    if ((e = put_lin(b.fc2, t[k + 8], t[k + 9], kC, 0, 0)) != cudaSuccess) return e;
+    k += 10;
+    return cudaSuccess;
+  };
+  auto put_cross = [&](const Block& b) -> cudaError_t {
+    cudaError_t e;
+    if ((e = put_f32(b.ctx_g, t[k], kC)) != cudaSuccess) return e;
+    if ((e = put_f32(b.ctx_b, t[k + 1], kC)) != cudaSuccess) return e;
+    if ((e = put_lin(b.q, t[k + 2], t[k + 3], kC, 0, 0)) != cudaSuccess) return e;
+    if ((e = put_lin(b.kv, t[k + 4], t[k + 5], 2 * kC, 0, 0)) != cudaSuccess) return e;
+    if ((e = put_lin(b.out, t[k + 6], t[k + 7], kC, 0, 0)) != cudaSuccess) return e;
+    if ((e = put_lin(b.fc1, t[k + 8], t[k + 9], kMlpHid, 0, 0)) != cudaSuccess) return e;
+    if ((e = put_lin(b.fc2, t[k + 10], t[k + 11], kC, 0, 0)) != cudaSuccess) return e;
+    k += 12;
+    return cudaSuccess;
+  };
+  for (int i = 0; i < kDepth; ++i) {
+    CK(put_self(L.time[i]), "pack time block");
+    CK(put_self(L.vself[i]), "pack virtual block");
+    CK(put_cross(L.p2v[i]), "pack point2virtual block");
+    CK(put_cross(L.v2p[i]), "pack virtual2point block");
+  }
+  return 0;
+}
+
+int ct3_pyramid_layout(int T, int H4, int W4, int64_t level_off[4], int level_h[4], int level_w[4],
+                       int64_t* total_floats) {
+  if (T < 1 || H4 < 1 || W4 < 1) return fail(CT3_EINVAL, "bad pyramid shape%s");
+  const PyramidLayout p = pyramid_layout(T, H4, W4);
+  for (int l = 0; l < kL; ++l) {
+    if (p.h[l] < 1 || p.w[l] < 1) return fail(CT3_EINVAL, "feature map too small for 4 pyramid levels%s");
+    if (level_off) level_off[l] = p.off[l];
+    if (level_h) level_h[l] = p.h[l];
+    if (level_w) level_w[l] = p.w[l];
+  }
+  if (total_floats) *total_floats = p.total;
+  return 0;
+}
+
+int ct3_prepare_pyramid(const float* fmaps, int T, int H4, int W4, float* pyr, ct3_stream_t stream) {
+  if (!fmaps || !pyr) return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  CK(launch_prepare_pyramid(fmaps, T, H4, W4, pyr, (cudaStream_t)stream), "prepare_pyramid");
+  return 0;
+}
+
+int ct3_sample_support(const float* pyr, int T, int H4, int W4, const int32_t* queried_frames,
+                       const float* queried_coords, int N, const uint8_t* accumulate_mask, float* support,
+                       ct3_stream_t stream) {
+  if (!pyr || !queried_frames || !queried_coords || !support) return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  if (N < 1) return fail(CT3_EINVAL, "N must be >= 1%s");
+  CK(launch_sample_support(pyr, T, H4, W4, queried_frames, queried_coords, N, accumulate_mask, support,
+                           (cudaStream_t)stream), "sample_support");
+  return 0;
+}
+
+int ct3_workspace_bytes(int T, int N, size_t* out_bytes) {
+  if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
+  if (int rc = check_TN(T, N)) return rc;
+  *out_bytes = carve(nullptr, T, N).total;
+  return 0;
+}
+
+int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support, const uint8_t* track_valid,
+                    const float* coords, int T, int N, void* vol_split, ct3_stream_t stream) {
+  if (!pyr || !support || !coords || !vol_split) return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = check_TN(T, N)) return rc;
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  CK(launch_corr_sample(pyr, H4, W4, support, track_valid, coords, T, N, (__nv_bfloat16*)vol_split, g_opt_corr,
+                        num_sms(), (cudaStream_t)stream), "corr_sample");
+  return 0;
+}
+
+int ct3_split_rows(const float* x, int rows, int K, int Kpad, void* x_split, ct3_stream_t stream) {
+  if (!x || !x_split || rows < 1 || K < 1 || Kpad < K || (Kpad % 64)) return fail(CT3_EINVAL, "bad split_rows argument%s");
+  CK(launch_split_rows(x, rows, K, Kpad, 0, (__nv_bfloat16*)x_split, 0, (cudaStream_t)stream), "split_rows");
+  return 0;
+}
+
+int ct3_linear(const void* x_split, const void* w_split, const float* bias, int M, int Nout, int Kpad, int act,
+               float* y, ct3_stream_t stream) {
+  if (!x_split || !w_split || !y) return fail(CT3_EINVAL, "null argument%s");
+  if (M < 1 || Nout < 1 || (Nout % 128) || Kpad < 64 || (Kpad % 64) || act < 0 || act > 2)
+    return fail(CT3_EINVAL, "ct3_linear: need M>=1, Nout %% 128 == 0, Kpad %% 64 == 0, act in 0..2%s");
+  GemmProblem p;
+  p.x_split = (const __nv_bfloat16*)x_split;
+  p.w_split = (const __nv_bfloat16*)w_split;
+  p.M = M; p.N = Nout; p.Kpad = Kpad;
+  p.epi.bias = bias;
+  p.epi.act = act;
+  p.epi.out_f32 = y;
+  p.epi.ld_f32 = Nout;
+  const char* gerr = nullptr;
+  int rc = gemm_launch(p, g_opt_gemm, num_sms(), (cudaStream_t)stream, &gerr);
+  if (rc != 0) {
+    snprintf(g_err, sizeof(g_err), "ct3_linear: %s (%s)", cudaGetErrorString((cudaError_t)rc), gerr ? gerr : "");
+    return CT3_ECUDA;
+  }
+  return 0;
+}
+
+int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const float* support,
+                    const uint8_t* track_valid, float* coords, float* vis, float* conf, const float* time_emb,
+                    int T, int N, int iters, void* workspace, size_t workspace_bytes, ct3_stream_t stream) {
+  if (!packed || !pyr || !support || !coords || !vis || !conf || !time_emb || !workspace)
+    return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = check_TN(T, N)) return rc;
+  if (iters < 0) return fail(CT3_EINVAL, "iters must be >= 0%s");
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  if ((uintptr_t)workspace & 1023) return fail(CT3_EINVAL, "workspace must be 1024-byte aligned%s");
+  const Workspace W = carve(workspace, T, N);
+  if (workspace_bytes < W.total) return fail(CT3_ENOSPC, "workspace too small%s");
+  const Layout& L = layout();
+  Runner R{reinterpret_cast<const uint8_t*>(packed), L, (cudaStream_t)stream, g_opt_gemm};
+  const uint8_t* pk = R.pk;
+  const int Rp = N * T, Mc = Rp * kL;
+
+  // W_in * time_emb[t]: x + time_emb is folded into a per-frame bias of input_transform (cotracker3_offline.py:196)
+  RUN(launch_row_bias(time_emb, reinterpret_cast<const float*>(pk + L.win_f32), T, W.row_bias, R.s));
+
+  for (int it = 0; it < iters; ++it) {
+    // (i)+(ii) sampling + 4-D correlation, all levels -> split volume
+    RUN(launch_corr_sample(pyr, H4, W4, support, track_valid, coords, T, N, W.vol, g_opt_corr, num_sms(), R.s));
+    // (iii) corr_mlp: 2401 -> 384 (GELU erf) -> 256, written straight into X columns [256*l, 256*l+256)
+    RUN(R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
+    {
+      GemmEpilogue e = Runner::to_split(W.xs, 2 * kXPad, kXPad, 0);
+      e.row_group = kL;
+      RUN(R.gemm(W.h1, L.corr_fc2, Mc, e));
+    }
+    // vis, conf, posenc(rel. motion), zero pad -> X columns [1024,1152)
+    RUN(launch_build_x_small(coords, vis, conf, T, N, W.xs, R.s));
+    // input_transform (+ folded time embedding) -> point tokens
+    {
+      GemmEpilogue e = Runner::to_f32(W.tokens, kC, false);
+      e.row_bias = W.row_bias;
+      e.row_mod = T;
+      RUN(R.gemm(W.xs, L.in_tr, Rp, e));
+    }
+    if (int rc = transformer_body(R, W, T, N)) return rc;
+    // (v) heads + state update
+    RUN(launch_heads(W.tokens, reinterpret_cast<const float*>(pk + L.heads_w),
+                     reinterpret_cast<const float*>(pk + L.heads_b), coords, vis, conf, nullptr, T, N, R.s));
+  }
+  return 0;
+}
+
+int ct3_updateformer(const void* packed, const float* x, int T, int N, float* delta, void* workspace,
+                     size_t workspace_bytes, ct3_stream_t stream) {
+  if (!packed || !x || !delta || !workspace) return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = check_TN(T, N)) return rc;
+  if ((uintptr_t)workspace & 1023) return fail(CT3_EINVAL, "workspace must be 1024-byte aligned%s");
+  const Workspace W = carve(workspace, T, N);
+  if (workspace_bytes < W.total) return fail(CT3_ENOSPC, "workspace too small%s");
+  const Layout& L = layout();
+  Runner R{reinterpret_cast<const uint8_t*>(packed), L, (cudaStream_t)stream, g_opt_gemm};
+  const int Rp = N * T;
+  RUN(launch_split_rows(x, Rp, kX, kXPad, /*perm_x*/ 1, W.xs, 0, R.s));
+  RUN(R.gemm(W.xs, L.in_tr, Rp, Runner::to_f32(W.tokens, kC, false)));
+  if (int rc = transformer_body(R, W, T, N)) return rc;
+  RUN(launch_heads(W.tokens, reinterpret_cast<const float*>(R.pk + L.heads_w),
+                   reinterpret_cast<const float*>(R.pk + L.heads_b), nullptr, nullptr, nullptr, delta, T, N, R.s));
+  return 0;
+}
+
+}  // extern "C"

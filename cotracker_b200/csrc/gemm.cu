@@ -1,0 +1,328 @@
+// gemm.cu -- split-bf16x3 linear layers on the 5th-gen tensor cores.
+//
+// Persistent warp-specialised kernel, one CTA per SM:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 3-stage ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per k16 step: hi*hi, lo*hi, hi*lo)
+//   warps 2..5  : epilogue       (tcgen05.ld -> bias / row-bias / GELU / residual -> fp32 and/or split-bf16 stores)
+// Two 128-column fp32 accumulators in TMEM are double buffered so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Tiles are 128 x 128; consecutive tile ids share the X (activation) tile so the
+// big operand is read from HBM once and hit in L2 by the CTAs working on its other N-tiles.
+//
+// A second, deliberately simple SIMT kernel computes the same contraction from the same split operands
+// (reconstructing hi+lo in fp32); tests use it to cross-check the tensor-core path on the GPU.
+#include "gemm.cuh"
+
+namespace ct3 {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 3, ACC = 2;
+constexpr int TILE_A = BM * BK * 2;                    // 16 KiB (bf16)
+constexpr int TILE_B = BN * BK * 2;                    // 16 KiB
+constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;   // hi+lo of both operands = 64 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr uint32_t TMEM_COLS = ACC * BN;               // 256 columns (power of two)
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return gelu_erf(x);
+  if (act == 2) return gelu_tanh(x);
+  return x;
+}
+
+// one thread = one output row, 32 consecutive columns starting at col0
+__device__ __forceinline__ void epilogue_store32(const GemmEpilogue& e, int N, int row, int col0, float (&v)[32]) {
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (e.row_bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.row_bias + (int64_t)(row % e.row_mod) * N + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+  }
+  if (e.act != 0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
+  }
+  if (e.out_f32) {
+    float4* o4 = reinterpret_cast<float4*>(e.out_f32 + (int64_t)row * e.ld_f32 + col0);
+    if (e.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 r = o4[i];
+        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (e.out_split) {
+    const int orow = row / e.row_group;
+    const int ocol = (row % e.row_group) * N + col0;
+    __nv_bfloat16* hp = e.out_split + (int64_t)orow * e.ld_split + ocol;
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    uint4* h4 = reinterpret_cast<uint4*>(hp);
+    uint4* l4 = reinterpret_cast<uint4*>(hp + e.lo_off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+      l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
+                      int N, int Kpad, GemmEpilogue epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_mt = (M + BM - 1) / BM;
+  const int num_nt = N / BN;
+  const int num_tiles = num_mt * num_nt;
+  const int num_kb = Kpad / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / num_nt, nt = tile % num_nt;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          tma_load_2d(s, &tmX, kb * BK, mt * BM, &full_bar[stage]);
+          tma_load_2d(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
+          tma_load_2d(s + 2 * TILE_A, &tmW, kb * BK, nt * BN, &full_bar[stage]);
+          tma_load_2d(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+          tc_fence_after_sync();
+          const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + 2 * TILE_A, b_lo = s + 2 * TILE_A + TILE_B;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint32_t koff = kk * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle atom
+            const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
+            const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
+            umma_bf16(d_tmem, dal, dbh, idesc, (kb | kk) != 0 ? 1u : 0u);  // small terms first
+            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (warps 2,3,4,5 -> 2,3,0,1)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / num_nt, nt = tile % num_nt;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row = mt * BM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        float v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32);
+        tmem_ld32(taddr, v);
+        if (row < M) epilogue_store32(epi, N, row, nt * BN + chunk * 32, v);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT verification kernel: 64x64 tile, 256 threads, each 4x4 outputs; fp32 FMA on hi+lo.
+__device__ __forceinline__ void epilogue_store1(const GemmEpilogue& e, int N, int row, int col, float v) {
+  if (e.bias) v += e.bias[col];
+  if (e.row_bias) v += e.row_bias[(int64_t)(row % e.row_mod) * N + col];
+  v = apply_act(v, e.act);
+  if (e.out_f32) {
+    float* o = e.out_f32 + (int64_t)row * e.ld_f32 + col;
+    if (e.residual) v += *o;
+    *o = v;
+  }
+  if (e.out_split) {
+    const int orow = row / e.row_group;
+    const int ocol = (row % e.row_group) * N + col;
+    bf16pair p = split_bf16(v);
+    __nv_bfloat16* hp = e.out_split + (int64_t)orow * e.ld_split + ocol;
+    hp[0] = p.hi;
+    hp[e.lo_off] = p.lo;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gemm_split3_simt_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ W, int M, int N,
+                        int Kpad, GemmEpilogue epi) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  const int64_t ld = 2 * (int64_t)Kpad;
+  for (int k0 = 0; k0 < Kpad; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      const int gm = m0 + r, gn = n0 + r;
+      float a = 0.f, b = 0.f;
+      if (gm < M) a = __bfloat162float(X[gm * ld + k0 + k]) + __bfloat162float(X[gm * ld + Kpad + k0 + k]);
+      if (gn < N) b = __bfloat162float(W[gn * ld + k0 + k]) + __bfloat162float(W[gn * ld + Kpad + k0 + k]);
+      As[k][r] = a;
+      Bs[k][r] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
+      if (r < M && c < N) epilogue_store1(epi, N, r, c, acc[i][j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] row-major, box = 64 cols (128 B) x 128 rows, 128-byte swizzle, OOB -> 0
+bool make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream, const char** err) {
+  *err = nullptr;
+  if (p.M <= 0 || p.N <= 0 || p.Kpad <= 0 || (p.N % BN) != 0 || (p.Kpad % BK) != 0) {
+    *err = "gemm: need M>0, N % 128 == 0, Kpad % 64 == 0";
+    return (int)cudaErrorInvalidValue;
+  }
+  if ((reinterpret_cast<uintptr_t>(p.x_split) | reinterpret_cast<uintptr_t>(p.w_split)) & 15) {
+    *err = "gemm: operands must be 16-byte aligned";
+    return (int)cudaErrorInvalidValue;
+  }
+  if (impl == 1) {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
+    gemm_split3_simt_kernel<<<grid, 256, 0, stream>>>(p.x_split, p.w_split, p.M, p.N, p.Kpad, p.epi);
+    return (int)cudaGetLastError();
+  }
+  CUtensorMap tmX, tmW;
+  if (!make_tmap(&tmX, p.x_split, (uint64_t)p.M, 2ull * p.Kpad) ||
+      !make_tmap(&tmW, p.w_split, (uint64_t)p.N, 2ull * p.Kpad)) {
+    *err = "gemm: cuTensorMapEncodeTiled failed";
+    return (int)cudaErrorInvalidValue;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed"; return (int)e; }
+    attr_set = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  gemm_split3_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.epi);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ct3

@@ -1,0 +1,40 @@
+// gemm.cuh -- interface of the split-bf16x3 linear-layer engine.
+//
+//   Y[M, N] = epilogue( X[M, K] * W[N, K]^T )      (nn.Linear; blocks.py:61-67, :375-377, cotracker.py:409-412)
+//
+// Operands are stored "split": X_split[M, 2*Kpad] = [hi(Kpad) | lo(Kpad)] bf16 with x = hi + lo,
+// likewise W_split[N, 2*Kpad].  The tensor cores accumulate hi*hi + lo*hi + hi*lo in fp32 (TMEM),
+// i.e. all first-order terms of the fp32 product (rel. error ~2^-17 per product, vs 2^-11 for TF32).
+#pragma once
+#include "common.cuh"
+
+namespace ct3 {
+
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N]
+  const float* row_bias = nullptr;  // [row_mod, N]; row r adds row_bias[(r % row_mod)]   (time-embedding fold)
+  int row_mod = 1;
+  int act = 0;                      // 0 none | 1 GELU(erf) | 2 GELU(tanh)
+  // fp32 output (optional): out_f32[r*ld_f32 + c] = v   or  += v  when residual
+  float* out_f32 = nullptr;
+  int64_t ld_f32 = 0;
+  int residual = 0;
+  // split bf16 output (optional): orow = r / row_group, ocol = (r % row_group) * N + c
+  //   hi -> out_split[orow*ld_split + ocol],  lo -> out_split[orow*ld_split + lo_off + ocol]
+  __nv_bfloat16* out_split = nullptr;
+  int64_t ld_split = 0;
+  int lo_off = 0;
+  int row_group = 1;
+};
+
+struct GemmProblem {
+  const __nv_bfloat16* x_split;  // [M, 2*Kpad]
+  const __nv_bfloat16* w_split;  // [N, 2*Kpad]
+  int M, N, Kpad;                // N % 128 == 0, Kpad % 64 == 0
+  GemmEpilogue epi;
+};
+
+// 0 = tcgen05 path, 1 = SIMT verification path.  Returns cudaError_t as int (0 = ok).
+int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream, const char** err);
+
+}  // namespace ct3

@@ -1,0 +1,51 @@
+// kernels.cuh -- launchers of the non-GEMM kernels of the update loop (definitions in *.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ct3 {
+
+// ---- prep.cu : per-clip preparation -------------------------------------------------------------
+struct PyramidLayout {
+  int64_t off[kL];  // float offset of each level inside the pyramid buffer
+  int h[kL], w[kL];
+  int64_t total;
+};
+PyramidLayout pyramid_layout(int T, int H4, int W4);
+cudaError_t launch_prepare_pyramid(const float* fmaps, int T, int H4, int W4, float* pyr, cudaStream_t s);
+cudaError_t launch_sample_support(const float* pyr, int T, int H4, int W4, const int32_t* qframes,
+                                  const float* qcoords, int N, const uint8_t* acc_mask, float* support,
+                                  cudaStream_t s);
+
+// ---- corr.cu : correlation sampling ---------------------------------------------------------------
+// vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level
+cudaError_t launch_corr_sample(const float* pyr, int H4, int W4, const float* support,
+                               const uint8_t* track_valid, const float* coords, int T, int N,
+                               __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s);
+
+// ---- tokens.cu : elementwise / row-wise pieces of the transformer ---------------------------------
+cudaError_t launch_layernorm_split(const float* x, int rows, const float* gamma, const float* beta, float eps,
+                                   __nv_bfloat16* out_split, cudaStream_t s);
+cudaError_t launch_build_x_small(const float* coords, const float* vis, const float* conf, int T, int N,
+                                 __nv_bfloat16* x_split, cudaStream_t s);
+cudaError_t launch_init_virtual(float* tokens, const float* virt, int T, int N, cudaStream_t s);
+// delta_out == nullptr: in-place state update; else write delta [N,T,4] and leave the state alone
+cudaError_t launch_heads(const float* tokens, const float* w4, const float* b4, float* coords, float* vis,
+                         float* conf, float* delta_out, int T, int N, cudaStream_t s);
+cudaError_t launch_row_bias(const float* time_emb, const float* w_in, int T, float* out, cudaStream_t s);
+// fp32 [rows,K] -> split [rows, 2*Kpad]; perm_x: apply the X column permutation (x_src_col)
+cudaError_t launch_split_rows(const float* x, int rows, int K, int Kpad, int perm_x, __nv_bfloat16* out,
+                              int64_t dst_row_off, cudaStream_t s);
+
+// ---- attention.cu -------------------------------------------------------------------------------
+struct AttnParams {
+  const float* q;  int64_t q_ld;  int q_col;
+  const float* kv; int64_t kv_ld; int k_col, v_col;
+  __nv_bfloat16* out; int64_t out_ld; int lo_off;
+  int num_seq, Lq, Lk;
+  int64_t q_seq_stride, q_tok_stride;  // q/out row = s*q_seq_stride + i*q_tok_stride
+  int64_t k_seq_stride, k_tok_stride;  // k/v row  = s*k_seq_stride + j*k_tok_stride
+  float scale;
+};
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);
+
+}  // namespace ct3

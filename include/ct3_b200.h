@@ -1,0 +1,156 @@
+/*
+ * ct3_b200.h -- C ABI of libct3_b200.so: the CoTracker3 iterative update loop
+ * (correlation sampling + correlation MLP + EfficientUpdateFormer + delta heads)
+ * as hand-written sm_100a CUDA.
+ *
+ * This is the drop-in boundary for the reference's inference hot path
+ * (citations are file:line inside facebookresearch/co-tracker):
+ *   cotracker/models/core/cotracker/cotracker3_offline.py:139-216   (offline loop body)
+ *   cotracker/models/core/cotracker/cotracker3_online.py:187-263    (forward_window loop body)
+ * and the per-clip preparation either side of it
+ *   cotracker3_offline.py:92-127  (L2-normalise, avg-pool pyramid, support sampling).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     name ends in _host; the caller (PyTorch) owns every allocation, the library
+ *     never allocates persistent device memory (scratch = caller workspace);
+ *   - every entry point returns 0 on success, a negative CT3_E* code otherwise,
+ *     never throws / exits; ct3_last_error() returns a thread-local message;
+ *   - all work is enqueued on the given cudaStream_t and is asynchronous w.r.t.
+ *     the host; B (batch) is 1 as in the reference (cotracker3_offline.py:135,141).
+ *
+ * Symbols (all extern "C"):  see the declarations below; tests/test_abi.py checks
+ * that the built library exports each of them.
+ */
+#ifndef CT3_B200_H_
+#define CT3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ct3_stream_t; /* == cudaStream_t */
+
+enum {
+  CT3_OK = 0,
+  CT3_EINVAL = -1,   /* bad argument (shape, null pointer, alignment)          */
+  CT3_ECUDA = -2,    /* a CUDA runtime/driver call failed (see ct3_last_error) */
+  CT3_ENOSPC = -3,   /* workspace / packed buffer too small                    */
+  CT3_EUNSUPPORTED = -4
+};
+
+/* Model constants fixed by the reference architecture
+ * (cotracker3_online.py:43-92, cotracker.py:392-462). */
+enum {
+  CT3_LATENT = 128,     /* feature channels D                                  */
+  CT3_LEVELS = 4,       /* corr_levels                                         */
+  CT3_RADIUS = 3,       /* corr_radius -> 7x7 = 49 samples                     */
+  CT3_P = 49,
+  CT3_VOL = 2401,       /* 49*49 correlation volume per (t,n,level)            */
+  CT3_VOL_PAD = 2432,   /* padded to a multiple of 64 for the tensor-core GEMM */
+  CT3_HID = 384,        /* transformer width C                                 */
+  CT3_HEADS = 8,
+  CT3_DHEAD = 48,
+  CT3_VIRT = 64,        /* virtual tracks                                      */
+  CT3_XDIM = 1110,      /* transformer input width                             */
+  CT3_XDIM_PAD = 1152,
+  CT3_DEPTH = 3         /* time_depth == space_depth                           */
+};
+
+/* Order of the fp32 tensors handed to ct3_pack_weights (names are the
+ * state-dict keys of the reference).  Per transformer
+ * layer i in [0,3) the block tensors follow in the order listed by
+ * ct3_weight_name(). */
+int ct3_num_weight_tensors(void);                 /* how many pointers ct3_pack_weights expects     */
+const char* ct3_weight_name(int index);           /* state-dict key of tensor #index (NULL if OOR)  */
+
+int ct3_version(void);
+const char* ct3_last_error(void);
+
+/* Debug/verification options ("gemm": 0 = tcgen05 tensor-core path (default),
+ * 1 = SIMT fp32 verification kernel used by the tests to cross-check). */
+int ct3_set_option(const char* name, int value);
+int ct3_get_option(const char* name, int* value);
+
+/* ---- one-time weight packing ------------------------------------------------
+ * Replaces the nn.Module parameter storage read by cotracker3_online.py:73-92.
+ * Splits every Linear weight into bf16 hi/lo planes ([out, 2*Kpad], K padded to
+ * a multiple of 64), concatenates to_q|to_kv for self-attention blocks, permutes
+ * the input_transform columns to the X layout documented in DESIGN.md. */
+int ct3_packed_weights_bytes(size_t* out_bytes);
+int ct3_pack_weights(const float* const* tensors_host_array_of_device_ptrs, int n_tensors,
+                     void* packed, size_t packed_bytes, ct3_stream_t stream);
+
+/* ---- per-clip preparation ---------------------------------------------------
+ * ct3_prepare_pyramid: cotracker3_offline.py:92-117 (L2-normalise over channels,
+ * 3x avg_pool2d(2,2)).  in: fnet output [T,128,H4,W4] fp32 channel-planar.
+ * out: pyr = 4 levels, channels-last [T,Hl,Wl,128] fp32, concatenated; level
+ * offsets (in floats) are returned by ct3_pyramid_layout. */
+int ct3_pyramid_layout(int T, int H4, int W4, int64_t level_off[4], int level_h[4], int level_w[4],
+                       int64_t* total_floats);
+int ct3_prepare_pyramid(const float* fmaps, int T, int H4, int W4, float* pyr, ct3_stream_t stream);
+
+/* ct3_sample_support: get_track_feat / sample_features5d
+ * (cotracker3_online.py:113-128, model_utils.py:293-323) for all 4 levels.
+ * queried_frames [N] int32 (already relative to the window, clamped into [0,T-1]),
+ * queried_coords [N,2] fp32 in stride-4 feature units (x,y).
+ * support out: [4][49,N,128] fp32 (the reference's [B,49,N,C] layout per level).
+ * If accumulate_mask != NULL ([N] uint8) the sampled features are ADDED to
+ * `support` where mask!=0 and nothing is written elsewhere (online accumulation,
+ * cotracker3_online.py:433-434); otherwise they overwrite. */
+int ct3_sample_support(const float* pyr, int T, int H4, int W4, const int32_t* queried_frames,
+                       const float* queried_coords, int N, const uint8_t* accumulate_mask,
+                       float* support, ct3_stream_t stream);
+
+/* ---- the hot loop -----------------------------------------------------------
+ * ct3_workspace_bytes: scratch needed by ct3_update_loop / ct3_update_iter. */
+int ct3_workspace_bytes(int T, int N, size_t* out_bytes);
+
+/* ct3_update_loop: `iters` refinement iterations, in place on the state.
+ *   packed   : ct3_pack_weights output
+ *   pyr      : ct3_prepare_pyramid output (T frames of the window)
+ *   support  : [4][49,N,128] fp32; track_valid (may be NULL) [N] uint8 zeroes the
+ *              support of not-yet-queried tracks (cotracker3_online.py:493-496)
+ *   coords   : [T,N,2] fp32 stride-4 feature units, in/out
+ *   vis,conf : [T,N] fp32 logits, in/out
+ *   time_emb : [T,1110] fp32 (buffer already interpolated to T,
+ *              cotracker3_online.py:145-156)
+ * On return coords/vis/conf hold the state after the last iteration (the caller
+ * multiplies coords by the stride and applies sigmoid, cotracker3_offline.py:213-216). */
+int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const float* support,
+                    const uint8_t* track_valid, float* coords, float* vis, float* conf,
+                    const float* time_emb, int T, int N, int iters, void* workspace,
+                    size_t workspace_bytes, ct3_stream_t stream);
+
+/* ---- stage-level entry points (used by the parity tests and profiles) ------- */
+
+/* Correlation sampling alone (get_correlation_feat + einsum,
+ * cotracker3_online.py:130-143, cotracker3_offline.py:144-156) for all levels:
+ * vol_split [N*T*4, 2*2432] bf16: row ((n*T+t)*4+level), hi plane cols [0,2432),
+ * lo plane cols [2432,4864); value = hi+lo, cols 2401..2431 are zero. */
+int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support,
+                    const uint8_t* track_valid, const float* coords, int T, int N,
+                    void* vol_split, ct3_stream_t stream);
+
+/* Generic split-bf16x3 linear layer  Y = act(X W^T + b)  (nn.Linear, blocks.py:61-67)
+ *   x_split [M, 2*Kpad] bf16 (hi|lo), w_split [Nout, 2*Kpad] bf16, bias [Nout] fp32 or NULL
+ *   act: 0 none, 1 GELU(erf), 2 GELU(tanh);  y fp32 [M, Nout] */
+int ct3_linear(const void* x_split, const void* w_split, const float* bias, int M, int Nout,
+               int Kpad, int act, float* y, ct3_stream_t stream);
+
+/* fp32 [rows, K] -> split bf16 [rows, 2*Kpad] (zero padded) */
+int ct3_split_rows(const float* x, int rows, int K, int Kpad, void* x_split, ct3_stream_t stream);
+
+/* One EfficientUpdateFormer forward (cotracker.py:483-531) on an explicit token
+ * input x [N, T, 1110] fp32 (time embedding already added, reference column order);
+ * delta out [N, T, 4] fp32. */
+int ct3_updateformer(const void* packed, const float* x, int T, int N, float* delta, void* workspace,
+                     size_t workspace_bytes, ct3_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CT3_B200_H_ */
