@@ -497,7 +497,7 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
   if (int rc = check_TN(T, N)) return rc;
   if (iters < 0) return fail(CT3_EINVAL, "iters must be >= 0%s");
   if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
-  if ((uintptr_t)workspace & 1023) return fail(CT3_EINVAL, "workspace must be 1024-byte aligned%s");
+  if ((uintptr_t)workspace & 255) return fail(CT3_EINVAL, "workspace must be 256-byte aligned%s");
   const Workspace W = carve(workspace, T, N);
   if (workspace_bytes < W.total) return fail(CT3_ENOSPC, "workspace too small%s");
   const Layout& L = layout();
@@ -539,7 +539,7 @@ int ct3_updateformer(const void* packed, const float* x, int T, int N, float* de
                      size_t workspace_bytes, ct3_stream_t stream) {
   if (!packed || !x || !delta || !workspace) return fail(CT3_EINVAL, "null argument%s");
   if (int rc = check_TN(T, N)) return rc;
-  if ((uintptr_t)workspace & 1023) return fail(CT3_EINVAL, "workspace must be 1024-byte aligned%s");
+  if ((uintptr_t)workspace & 255) return fail(CT3_EINVAL, "workspace must be 256-byte aligned%s");
   const Workspace W = carve(workspace, T, N);
   if (workspace_bytes < W.total) return fail(CT3_ENOSPC, "workspace too small%s");
   const Layout& L = layout();

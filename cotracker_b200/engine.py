@@ -1,0 +1,272 @@
+"""ctypes binding of libct3_b200.so (C ABI: include/ct3_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every tensor is handed to the
+library as a raw device pointer.  There is NO fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised (the product path never routes through the oracle or eager PyTorch).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libct3_b200.so")
+
+LATENT, LEVELS, P, VOL, VOL_PAD = 128, 4, 49, 2401, 2432
+HID, VIRT, XDIM, XDIM_PAD = 384, 64, 1110, 1152
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    c_int, c_size_t, c_void_p, c_char_p = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_char_p
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    intp = ctypes.POINTER(ctypes.c_int)
+    sig = {
+        "ct3_version": (c_int, []),
+        "ct3_last_error": (c_char_p, []),
+        "ct3_set_option": (c_int, [c_char_p, c_int]),
+        "ct3_get_option": (c_int, [c_char_p, intp]),
+        "ct3_num_weight_tensors": (c_int, []),
+        "ct3_weight_name": (c_char_p, [c_int]),
+        "ct3_packed_weights_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
+        "ct3_pack_weights": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_size_t, c_void_p]),
+        "ct3_pyramid_layout": (c_int, [c_int, c_int, c_int, i64p, intp, intp, i64p]),
+        "ct3_prepare_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_sample_support": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+        "ct3_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
+        "ct3_update_loop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+        "ct3_corr_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_split_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_updateformer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTED_SYMBOLS = [
+    "ct3_version", "ct3_last_error", "ct3_set_option", "ct3_get_option", "ct3_num_weight_tensors",
+    "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
+    "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
+    "ct3_corr_sample", "ct3_linear", "ct3_split_rows", "ct3_updateformer",
+]
+
+
+def lib():
+    """Load (once) and return the shared library; raises EngineError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C cotracker_b200/csrc`). There is no CPU/eager fallback.")
+        try:
+            handle = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise EngineError(f"cannot load {LIB_PATH}: {e}") from e
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().ct3_last_error().decode("utf-8", "replace")
+        raise EngineError(f"{what} failed (code {rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise EngineError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise EngineError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise EngineError(f"{name} must be contiguous")
+    return t
+
+
+def set_option(name: str, value: int):
+    _check(lib().ct3_set_option(name.encode(), int(value)), f"ct3_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = ctypes.c_int(0)
+    _check(lib().ct3_get_option(name.encode(), ctypes.byref(v)), f"ct3_get_option({name})")
+    return v.value
+
+
+def weight_names() -> List[str]:
+    L = lib()
+    return [L.ct3_weight_name(i).decode() for i in range(L.ct3_num_weight_tensors())]
+
+
+def packed_weights_bytes() -> int:
+    n = ctypes.c_size_t(0)
+    _check(lib().ct3_packed_weights_bytes(ctypes.byref(n)), "ct3_packed_weights_bytes")
+    return n.value
+
+
+def pack_weights(state: dict, device) -> torch.Tensor:
+    """state: mapping state-dict key -> tensor (any device); returns the packed device buffer."""
+    names = weight_names()
+    tensors = []
+    for k in names:
+        if k not in state:
+            raise EngineError(f"missing weight '{k}'")
+        tensors.append(state[k].detach().to(device=device, dtype=torch.float32).contiguous())
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    nbytes = packed_weights_bytes()
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _check(lib().ct3_pack_weights(arr, len(tensors), _ptr(packed), nbytes, _stream(device)), "ct3_pack_weights")
+        torch.cuda.current_stream(device).synchronize()  # `tensors` may be temporaries
+    return packed
+
+
+def pyramid_layout(T: int, H4: int, W4: int):
+    off = (ctypes.c_int64 * 4)()
+    h = (ctypes.c_int * 4)()
+    w = (ctypes.c_int * 4)()
+    tot = ctypes.c_int64(0)
+    _check(lib().ct3_pyramid_layout(T, H4, W4, off, h, w, ctypes.byref(tot)), "ct3_pyramid_layout")
+    return list(off), list(h), list(w), tot.value
+
+
+def prepare_pyramid(fmaps: torch.Tensor) -> torch.Tensor:
+    """fmaps [T,128,H4,W4] fp32 (raw fnet output) -> flat channels-last normalised 4-level pyramid."""
+    _req(fmaps, torch.float32, "fmaps")
+    T, C, H4, W4 = fmaps.shape
+    if C != LATENT:
+        raise EngineError("fmaps must have 128 channels")
+    *_, total = pyramid_layout(T, H4, W4)
+    pyr = torch.empty(total, dtype=torch.float32, device=fmaps.device)
+    with torch.cuda.device(fmaps.device):
+        _check(lib().ct3_prepare_pyramid(_ptr(fmaps), T, H4, W4, _ptr(pyr), _stream(fmaps.device)), "ct3_prepare_pyramid")
+    return pyr
+
+
+def pyramid_levels(pyr: torch.Tensor, T: int, H4: int, W4: int) -> List[torch.Tensor]:
+    """Views [T,Hl,Wl,128] into the flat pyramid (tests / debugging)."""
+    off, h, w, _ = pyramid_layout(T, H4, W4)
+    return [pyr[off[l]: off[l] + T * h[l] * w[l] * LATENT].view(T, h[l], w[l], LATENT) for l in range(LEVELS)]
+
+
+def sample_support(pyr, T, H4, W4, qframes, qcoords, support=None, accumulate_mask=None) -> torch.Tensor:
+    _req(pyr, torch.float32, "pyr")
+    _req(qframes, torch.int32, "queried_frames")
+    _req(qcoords, torch.float32, "queried_coords")
+    N = qframes.shape[0]
+    if support is None:
+        support = torch.zeros(LEVELS, P, N, LATENT, dtype=torch.float32, device=pyr.device)
+    _req(support, torch.float32, "support")
+    if accumulate_mask is not None:
+        _req(accumulate_mask, torch.uint8, "accumulate_mask")
+    with torch.cuda.device(pyr.device):
+        _check(lib().ct3_sample_support(_ptr(pyr), T, H4, W4, _ptr(qframes), _ptr(qcoords), N, _ptr(accumulate_mask),
+                                        _ptr(support), _stream(pyr.device)), "ct3_sample_support")
+    return support
+
+
+def workspace_bytes(T: int, N: int) -> int:
+    n = ctypes.c_size_t(0)
+    _check(lib().ct3_workspace_bytes(T, N, ctypes.byref(n)), "ct3_workspace_bytes")
+    return n.value
+
+
+class WorkspaceCache:
+    """Caller-owned scratch, grown on demand (the library never allocates)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, T: int, N: int, device) -> torch.Tensor:
+        need = workspace_bytes(T, N)
+        if self.buf is None or self.buf.numel() < need or self.buf.device != torch.device(device):
+            self.buf = None
+            self.buf = torch.empty(need, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+def update_loop(packed, pyr, H4, W4, support, track_valid, coords, vis, conf, time_emb, iters, workspace):
+    """In-place refinement of coords [T,N,2], vis [T,N], conf [T,N] (fp32, feature-grid units / logits)."""
+    _req(coords, torch.float32, "coords"); _req(vis, torch.float32, "vis"); _req(conf, torch.float32, "conf")
+    _req(pyr, torch.float32, "pyr"); _req(support, torch.float32, "support"); _req(time_emb, torch.float32, "time_emb")
+    T, N, _ = coords.shape
+    if time_emb.shape != (T, XDIM):
+        raise EngineError(f"time_emb must be [{T},{XDIM}]")
+    if track_valid is not None:
+        _req(track_valid, torch.uint8, "track_valid")
+    with torch.cuda.device(coords.device):
+        _check(lib().ct3_update_loop(_ptr(packed), _ptr(pyr), H4, W4, _ptr(support), _ptr(track_valid), _ptr(coords),
+                                     _ptr(vis), _ptr(conf), _ptr(time_emb), T, N, int(iters), _ptr(workspace),
+                                     workspace.numel(), _stream(coords.device)), "ct3_update_loop")
+
+
+# ---- stage-level wrappers (tests, profiles) -----------------------------------------------------------
+def corr_sample(pyr, H4, W4, support, track_valid, coords) -> torch.Tensor:
+    """-> fp32 correlation volume [N, T, 4, 2401] reconstructed from the split-bf16 device layout."""
+    T, N, _ = coords.shape
+    vol = torch.empty(N * T * LEVELS, 2 * VOL_PAD, dtype=torch.bfloat16, device=coords.device)
+    with torch.cuda.device(coords.device):
+        _check(lib().ct3_corr_sample(_ptr(pyr), H4, W4, _ptr(support), _ptr(track_valid), _ptr(coords), T, N, _ptr(vol),
+                                     _stream(coords.device)), "ct3_corr_sample")
+    v = vol.float()
+    full = v[:, :VOL_PAD] + v[:, VOL_PAD:]
+    assert bool((full[:, VOL:] == 0).all()), "K padding of the correlation volume must be zero"
+    return full[:, :VOL].reshape(N, T, LEVELS, VOL)
+
+
+def split_rows(x: torch.Tensor, Kpad: int) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    rows, K = x.shape
+    out = torch.empty(rows, 2 * Kpad, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().ct3_split_rows(_ptr(x), rows, K, Kpad, _ptr(out), _stream(x.device)), "ct3_split_rows")
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
+    """Y = act(x w^T + b) through the split-bf16x3 engine; x [M,K], w [Nout,K] fp32."""
+    M, K = x.shape
+    Nout = w.shape[0]
+    Kpad = (K + 63) // 64 * 64
+    xs, ws = split_rows(x.contiguous(), Kpad), split_rows(w.contiguous(), Kpad)
+    y = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().ct3_linear(_ptr(xs), _ptr(ws), _ptr(bias), M, Nout, Kpad, act, _ptr(y), _stream(x.device)), "ct3_linear")
+    return y
+
+
+def updateformer(packed, x: torch.Tensor, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [N,T,1110] fp32 (reference column order, time embedding added) -> delta [N,T,4]."""
+    _req(x, torch.float32, "x")
+    N, T, D = x.shape
+    if D != XDIM:
+        raise EngineError("x must be [N,T,1110]")
+    if workspace is None:
+        workspace = torch.empty(workspace_bytes(T, N), dtype=torch.uint8, device=x.device)
+    delta = torch.empty(N, T, 4, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().ct3_updateformer(_ptr(packed), _ptr(x), T, N, _ptr(delta), _ptr(workspace), workspace.numel(),
+                                      _stream(x.device)), "ct3_updateformer")
+    return delta

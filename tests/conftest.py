@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def reference_path():
+    """Path of the unmodified reference checkout (build container only)."""
+    p = os.environ.get("COTRACKER_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(p, "cotracker")):
+        pytest.skip("reference checkout not present on this machine")
+    return p

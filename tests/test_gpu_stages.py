@@ -1,0 +1,195 @@
+"""GPU stage-level parity: every CUDA kernel against the CPU oracle (called through the C ABI).
+Amplified inputs/weights are used where end-to-end parity is blind."""
+import math
+
+import pytest
+import torch
+
+from cases import O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from cotracker_b200 import engine
+    engine.lib()
+    engine.set_option("gemm", 0)
+    return engine
+
+
+def _rel_err(got, want):
+    return float((got.double().cpu() - want.double().cpu()).abs().max() / (want.double().abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 384, 384), (1000, 2401, 384), (257, 1110, 384),
+                                   (640, 1536, 384), (4100, 384, 1536), (129, 384, 256), (64, 384, 1152)])
+def test_linear_matches_fp64(eng, impl, M, K, N):
+    g = torch.Generator().manual_seed(M * 7 + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    want = x.double() @ w.double().t() + b.double()
+    eng.set_option("gemm", impl)
+    try:
+        got = eng.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=0)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("gemm", 0)
+    # split-bf16x3: ~2^-17 per product; fp32 accumulate.  fp32 SIMT: ~1e-6.
+    assert _rel_err(got, want) < 2e-5, (impl, M, K, N, _rel_err(got, want))
+
+
+@pytest.mark.parametrize("act,approx", [(1, "none"), (2, "tanh")])
+def test_linear_gelu_epilogues(eng, act, approx):
+    g = torch.Generator().manual_seed(act)
+    x = torch.randn(513, 384, generator=g) * 3
+    w = torch.randn(384, 384, generator=g) / 10
+    b = torch.randn(384, generator=g)
+    want = torch.nn.functional.gelu((x.double() @ w.double().t() + b.double()), approximate=approx)
+    got = eng.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=act)
+    assert _rel_err(got, want) < 2e-5
+
+
+def _pyramid_case(T=3, H4=24, W4=32, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    fmaps = torch.randn(T, 128, H4, W4, generator=g) * 2.5
+    fmaps[0, :, 0, 0] = 0.0  # zero vector -> the 1e-12 clamp path
+    return fmaps
+
+
+def test_prepare_pyramid(eng):
+    T, H4, W4 = 3, 25, 33  # odd sizes: avg-pool floors
+    fmaps = _pyramid_case(T, H4, W4)
+    want = O.normalized_pyramid(fmaps)
+    pyr = eng.prepare_pyramid(fmaps.to(DEV))
+    levels = eng.pyramid_levels(pyr, T, H4, W4)
+    for l in range(4):
+        got = levels[l].permute(0, 3, 1, 2).cpu()
+        assert got.shape == want[l].shape
+        assert float((got - want[l]).abs().max()) < 1e-6, l
+
+
+def _coords_case(T, N, H4, W4, seed):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(T, N, 2, generator=g) * torch.tensor([W4 - 1.0, H4 - 1.0])
+    c[:, 0] = torch.tensor([-7.3, -2.0])                 # far outside: everything clamps
+    c[:, 1] = torch.tensor([W4 + 5.5, H4 + 9.25])
+    c[:, 2] = torch.tensor([0.0, 0.0])
+    c[:, 3] = torch.tensor([W4 - 1.0, H4 - 1.0])         # exactly on the last texel
+    c[:, 4] = torch.tensor([2.5, H4 - 1.75])
+    return c
+
+
+def test_sample_support(eng):
+    T, H4, W4, N = 4, 24, 32, 40
+    fmaps = _pyramid_case(T, H4, W4, seed=1)
+    want_pyr = O.normalized_pyramid(fmaps)
+    pyr = eng.prepare_pyramid(fmaps.to(DEV))
+    g = torch.Generator().manual_seed(3)
+    qf = torch.randint(0, T, (N,), generator=g)
+    qc = _coords_case(1, N, H4, W4, 5)[0]
+    got = eng.sample_support(pyr, T, H4, W4, qf.to(torch.int32).to(DEV), qc.to(DEV)).cpu()
+    for l in range(4):
+        want = O.support_features(want_pyr[l], qf, qc / 2 ** l)
+        assert float((got[l] - want).abs().max()) < 2e-5, l
+    # online accumulation: masked add
+    acc = torch.ones(4, 49, N, 128, device=DEV)
+    mask = (torch.arange(N) % 3 == 0).to(torch.uint8)
+    eng.sample_support(pyr, T, H4, W4, qf.to(torch.int32).to(DEV), qc.to(DEV), support=acc, accumulate_mask=mask.to(DEV))
+    acc = acc.cpu()
+    sel = mask.bool()
+    assert float((acc[:, :, sel] - 1 - got[:, :, sel]).abs().max()) < 1e-6
+    assert bool((acc[:, :, ~sel] == 1).all())
+
+
+@pytest.mark.parametrize("T,N,H4,W4", [(3, 16, 24, 32), (2, 9, 8, 8), (5, 33, 96, 128)])
+def test_corr_sample(eng, T, N, H4, W4):
+    fmaps = _pyramid_case(T, H4, W4, seed=2)
+    want_pyr = O.normalized_pyramid(fmaps)
+    pyr = eng.prepare_pyramid(fmaps.to(DEV))
+    g = torch.Generator().manual_seed(11)
+    support = torch.randn(4, 49, N, 128, generator=g)
+    support = support / support.norm(dim=-1, keepdim=True)
+    coords = _coords_case(T, N, H4, W4, 13)
+    valid = torch.ones(N, dtype=torch.uint8)
+    valid[5] = 0
+    got = eng.corr_sample(pyr, H4, W4, support.to(DEV), valid.to(DEV), coords.to(DEV)).cpu()   # [N,T,4,2401]
+    for l in range(4):
+        want = O.correlation_volume(want_pyr[l], support[l] * valid[None, :, None].float(), coords / 2 ** l)  # [T,N,2401]
+        err = float((got[:, :, l].permute(1, 0, 2) - want).abs().max())
+        assert err < 3e-5, (l, err)      # |corr| <= 1; grid_sample's normalise/denormalise noise ~1e-5
+    assert bool((got[5] == 0).all())
+
+
+def _amplified_sd(seed=1234, **kw):
+    from cotracker_b200.synthetic import seeded_state_dict
+    return seeded_state_dict(seed, offline=True, window_len=60, **kw)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_updateformer_stage(eng, impl):
+    sd = _amplified_sd(head_gain=100.0, vis_gain=100.0)
+    g = torch.Generator().manual_seed(21)
+    N, T = 70, 6
+    x = torch.randn(N, T, 1110, generator=g)
+    with torch.no_grad():
+        want = O.updateformer(sd, x[None])[0]
+    packed = eng.pack_weights(sd, DEV)
+    eng.set_option("gemm", impl)
+    try:
+        got = eng.updateformer(packed, x.to(DEV)).cpu()
+    finally:
+        eng.set_option("gemm", 0)
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max())
+    assert err < 2e-4 * max(scale, 1.0), (err, scale)
+
+
+def test_corr_mlp_gelu_variant_is_erf(eng):
+    """Mutation guard: with volume x10 the erf and tanh GELUs differ by >1e-3."""
+    sd = _amplified_sd()
+    g = torch.Generator().manual_seed(5)
+    vol = (torch.rand(256, 2401, generator=g) * 2 - 1) * 10
+    with torch.no_grad():
+        h_erf = torch.nn.functional.gelu(torch.nn.functional.linear(vol, sd["corr_mlp.fc1.weight"], sd["corr_mlp.fc1.bias"]))
+        h_tanh = torch.nn.functional.gelu(torch.nn.functional.linear(vol, sd["corr_mlp.fc1.weight"], sd["corr_mlp.fc1.bias"]), approximate="tanh")
+    assert float((h_erf - h_tanh).abs().max()) > 1e-4
+    got = eng.linear(vol.to(DEV), sd["corr_mlp.fc1.weight"].to(DEV), sd["corr_mlp.fc1.bias"].to(DEV), act=1).cpu()
+    assert float((got - h_erf).abs().max()) < 0.2 * float((h_erf - h_tanh).abs().max())
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_update_loop_vs_oracle(eng, impl):
+    """The hot loop alone: identical pyramid/support on both sides, amplified heads (several px of motion)."""
+    sd = _amplified_sd(seed=7, head_gain=10.0, vis_gain=100.0)
+    T, N, H4, W4, iters = 7, 37, 24, 32, 4
+    fmaps = _pyramid_case(T, H4, W4, seed=4)
+    pyr_cpu = O.normalized_pyramid(fmaps)
+    g = torch.Generator().manual_seed(31)
+    qf = torch.randint(0, T, (N,), generator=g)
+    qc = _coords_case(1, N, H4, W4, 17)[0]
+    sup_cpu = [O.support_features(pyr_cpu[l], qf, qc / 2 ** l) for l in range(4)]
+    c0 = qc[None].expand(T, N, 2).contiguous()
+    with torch.no_grad():
+        wc, wv, wq = O.update_loop(sd, pyr_cpu, sup_cpu, c0, torch.zeros(T, N), torch.zeros(T, N), iters)
+    pyr = eng.prepare_pyramid(fmaps.to(DEV))
+    support = torch.stack(sup_cpu).to(DEV).contiguous()
+    packed = eng.pack_weights(sd, DEV)
+    coords, vis, conf = c0.to(DEV).clone(), torch.zeros(T, N, device=DEV), torch.zeros(T, N, device=DEV)
+    ws = torch.empty(eng.workspace_bytes(T, N), dtype=torch.uint8, device=DEV)
+    te = O.time_embedding(sd, T)[0].contiguous().to(DEV)
+    eng.set_option("gemm", impl)
+    try:
+        eng.update_loop(packed, pyr, H4, W4, support, None, coords, vis, conf, te, iters, ws)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("gemm", 0)
+    assert float((wc - c0).abs().max()) > 0.25, "case must move"
+    e_c = float((coords.cpu() - wc).abs().max()) * 4  # pixels
+    e_v = float((vis.cpu() - wv).abs().max())
+    e_q = float((conf.cpu() - wq).abs().max())
+    print("loop parity", impl, e_c, e_v, e_q)
+    assert e_c < 1e-3 and e_v < 1e-3 and e_q < 1e-3
