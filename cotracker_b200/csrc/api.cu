@@ -42,6 +42,23 @@ int num_sms() {
   return n;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// optional live profiler: CUDA events around every launch, summed per kernel category (bench.py roofline)
+enum { CAT_CORR = 0, CAT_GEMM = 1, CAT_ATTN = 2, CAT_LN = 3, CAT_MISC = 4, CAT_COUNT = 5 };
+struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t s; int cat; double flops; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(cudaStream_t s_, int cat_, double flops_ = 0.0) : s(s_), cat(cat_), flops(flops_) {
+    if (g_prof_on && cat_ >= 0) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+  }
+  ~ProfScope() {
+    if (a) { cudaEventRecord(b, s); g_prof.push_back({cat, a, b, flops}); }
+  }
+};
+
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
@@ -194,6 +211,7 @@ struct Runner {
     p.epi = e;
     if (!p.epi.bias) p.epi.bias = reinterpret_cast<const float*>(pk + lin.b);
     if (M == 0) return 0;
+    ProfScope ps(s, CAT_GEMM, 2.0 * (double)M * lin.N * lin.K);
     return gemm_launch(p, impl, num_sms(), s, &gerr);
   }
   static GemmEpilogue to_f32(float* out, int ld, bool residual) {
@@ -208,9 +226,10 @@ struct Runner {
   }
 };
 
-#define RUN(call)                                                                        \
+#define RUNC(cat, call)                                                                  \
   do {                                                                                   \
-    int rc__ = (int)(call);                                                              \
+    int rc__;                                                                            \
+    { ProfScope ps__(R.s, cat); rc__ = (int)(call); }                                    \
     if (rc__ != 0) {                                                                     \
       snprintf(g_err, sizeof(g_err), "%s failed: %s (%s)", #call,                        \
                cudaGetErrorString((cudaError_t)rc__), R.gerr ? R.gerr : "");             \
@@ -223,9 +242,9 @@ int mlp_half(Runner& R, const Workspace& W, const Block& b, int64_t row0, int ro
   float* x = W.tokens + row0 * kC;
   __nv_bfloat16* ln = W.ln + row0 * 2 * kC;
   __nv_bfloat16* hm = W.hmid + row0 * 2 * kMlpHid;
-  RUN(launch_layernorm_split(x, rows, nullptr, nullptr, 1e-6f, ln, R.s));
-  RUN(R.gemm(ln, b.fc1, rows, Runner::to_split(hm, 2 * kMlpHid, kMlpHid, /*tanh*/ 2)));
-  RUN(R.gemm(hm, b.fc2, rows, Runner::to_f32(x, kC, true)));
+  RUNC(CAT_LN, launch_layernorm_split(x, rows, nullptr, nullptr, 1e-6f, ln, R.s));
+  RUNC(-1, R.gemm(ln, b.fc1, rows, Runner::to_split(hm, 2 * kMlpHid, kMlpHid, /*tanh*/ 2)));
+  RUNC(-1, R.gemm(hm, b.fc2, rows, Runner::to_f32(x, kC, true)));
   return 0;
 }
 
@@ -235,7 +254,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
   const int Rp = N * T, Rv = kV * T, Rall = Rp + Rv;
   const float scale = 1.0f / sqrtf((float)kDh);
   const uint8_t* pk = R.pk;
-  RUN(launch_init_virtual(W.tokens, reinterpret_cast<const float*>(pk + L.virt), T, N, R.s));
+  RUNC(CAT_MISC, launch_init_virtual(W.tokens, reinterpret_cast<const float*>(pk + L.virt), T, N, R.s));
   float* vtok = W.tokens + (int64_t)Rp * kC;
   __nv_bfloat16* ln_p = W.ln;
   __nv_bfloat16* ln_v = W.ln + (int64_t)Rp * 2 * kC;
@@ -245,8 +264,8 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
   for (int i = 0; i < kDepth; ++i) {
     {  // ---- time block over every token row (points + virtual): sequence = track (cotracker.py:494-495)
       const Block& b = L.time[i];
-      RUN(launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
-      RUN(R.gemm(W.ln, b.q, Rall, Runner::to_f32(W.qkv, 3 * kC, false)));
+      RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
+      RUNC(-1, R.gemm(W.ln, b.q, Rall, Runner::to_f32(W.qkv, 3 * kC, false)));
       AttnParams a{};
       a.q = W.qkv; a.q_ld = 3 * kC; a.q_col = 0;
       a.kv = W.qkv; a.kv_ld = 3 * kC; a.k_col = kC; a.v_col = 2 * kC;
@@ -254,17 +273,17 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = N + kV; a.Lq = T; a.Lk = T;
       a.q_seq_stride = T; a.q_tok_stride = 1; a.k_seq_stride = T; a.k_tok_stride = 1;
       a.scale = scale;
-      RUN(launch_attention(a, R.s));
-      RUN(R.gemm(W.att, b.out, Rall, Runner::to_f32(W.tokens, kC, true)));
+      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(-1, R.gemm(W.att, b.out, Rall, Runner::to_f32(W.tokens, kC, true)));
       if (int rc = mlp_half(R, W, b, 0, Rall)) return rc;
     }
     {  // ---- virtual <- point cross attention (cotracker.py:510-512): x = virtual, context = points
       const Block& b = L.v2p[i];
-      RUN(launch_layernorm_split(vtok, Rv, nullptr, nullptr, 1e-6f, ln_v, R.s));
-      RUN(launch_layernorm_split(W.tokens, Rp, reinterpret_cast<const float*>(pk + b.ctx_g),
+      RUNC(CAT_LN, launch_layernorm_split(vtok, Rv, nullptr, nullptr, 1e-6f, ln_v, R.s));
+      RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rp, reinterpret_cast<const float*>(pk + b.ctx_g),
                                  reinterpret_cast<const float*>(pk + b.ctx_b), 1e-5f, ln_p, R.s));
-      RUN(R.gemm(ln_v, b.q, Rv, Runner::to_f32(W.vqkv, kC, false)));
-      RUN(R.gemm(ln_p, b.kv, Rp, Runner::to_f32(W.qkv, 2 * kC, false)));
+      RUNC(-1, R.gemm(ln_v, b.q, Rv, Runner::to_f32(W.vqkv, kC, false)));
+      RUNC(-1, R.gemm(ln_p, b.kv, Rp, Runner::to_f32(W.qkv, 2 * kC, false)));
       AttnParams a{};
       a.q = W.vqkv; a.q_ld = kC; a.q_col = 0;
       a.kv = W.qkv; a.kv_ld = 2 * kC; a.k_col = 0; a.v_col = kC;
@@ -272,14 +291,14 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = T; a.Lq = kV; a.Lk = N;
       a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
       a.scale = scale;
-      RUN(launch_attention(a, R.s));
-      RUN(R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
+      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(-1, R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
       if (int rc = mlp_half(R, W, b, Rp, Rv)) return rc;
     }
     {  // ---- virtual self attention (cotracker.py:514): sequence = frame over the 64 virtual tokens
       const Block& b = L.vself[i];
-      RUN(launch_layernorm_split(vtok, Rv, nullptr, nullptr, 1e-6f, ln_v, R.s));
-      RUN(R.gemm(ln_v, b.q, Rv, Runner::to_f32(W.vqkv, 3 * kC, false)));
+      RUNC(CAT_LN, launch_layernorm_split(vtok, Rv, nullptr, nullptr, 1e-6f, ln_v, R.s));
+      RUNC(-1, R.gemm(ln_v, b.q, Rv, Runner::to_f32(W.vqkv, 3 * kC, false)));
       AttnParams a{};
       a.q = W.vqkv; a.q_ld = 3 * kC; a.q_col = 0;
       a.kv = W.vqkv; a.kv_ld = 3 * kC; a.k_col = kC; a.v_col = 2 * kC;
@@ -287,17 +306,17 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = T; a.Lq = kV; a.Lk = kV;
       a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
       a.scale = scale;
-      RUN(launch_attention(a, R.s));
-      RUN(R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
+      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(-1, R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
       if (int rc = mlp_half(R, W, b, Rp, Rv)) return rc;
     }
     {  // ---- point <- virtual cross attention (cotracker.py:515-517): x = points, context = virtual
       const Block& b = L.p2v[i];
-      RUN(launch_layernorm_split(W.tokens, Rp, nullptr, nullptr, 1e-6f, ln_p, R.s));
-      RUN(launch_layernorm_split(vtok, Rv, reinterpret_cast<const float*>(pk + b.ctx_g),
+      RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rp, nullptr, nullptr, 1e-6f, ln_p, R.s));
+      RUNC(CAT_LN, launch_layernorm_split(vtok, Rv, reinterpret_cast<const float*>(pk + b.ctx_g),
                                  reinterpret_cast<const float*>(pk + b.ctx_b), 1e-5f, ln_v, R.s));
-      RUN(R.gemm(ln_p, b.q, Rp, Runner::to_f32(W.qkv, kC, false)));
-      RUN(R.gemm(ln_v, b.kv, Rv, Runner::to_f32(W.vqkv, 2 * kC, false)));
+      RUNC(-1, R.gemm(ln_p, b.q, Rp, Runner::to_f32(W.qkv, kC, false)));
+      RUNC(-1, R.gemm(ln_v, b.kv, Rv, Runner::to_f32(W.vqkv, 2 * kC, false)));
       AttnParams a{};
       a.q = W.qkv; a.q_ld = kC; a.q_col = 0;
       a.kv = W.vqkv; a.kv_ld = 2 * kC; a.k_col = 0; a.v_col = kC;
@@ -305,8 +324,8 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = T; a.Lq = N; a.Lk = kV;
       a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
       a.scale = scale;
-      RUN(launch_attention(a, R.s));
-      RUN(R.gemm(att_p, b.out, Rp, Runner::to_f32(W.tokens, kC, true)));
+      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(-1, R.gemm(att_p, b.out, Rp, Runner::to_f32(W.tokens, kC, true)));
       if (int rc = mlp_half(R, W, b, 0, Rp)) return rc;
     }
   }
@@ -444,6 +463,28 @@ int ct3_sample_support(const float* pyr, int T, int H4, int W4, const int32_t* q
   return 0;
 }
 
+int ct3_profile_enable(int on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return 0;
+}
+// ms[5], launches[5], gemm_flops: sums since ct3_profile_enable(1); synchronises the recorded events
+int ct3_profile_read(double* ms, int* launches, double* gemm_flops) {
+  if (!ms || !launches || !gemm_flops) return fail(CT3_EINVAL, "null argument%s");
+  for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  *gemm_flops = 0.0;
+  for (auto& r : g_prof) {
+    CK(cudaEventSynchronize(r.b), "profile sync");
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b), "profile elapsed");
+    ms[r.cat] += t;
+    launches[r.cat] += 1;
+    *gemm_flops += r.flops;
+  }
+  return 0;
+}
+
 int ct3_workspace_bytes(int T, int N, size_t* out_bytes) {
   if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
   if (int rc = check_TN(T, N)) return rc;
@@ -506,30 +547,30 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
   const int Rp = N * T, Mc = Rp * kL;
 
   // W_in * time_emb[t]: x + time_emb is folded into a per-frame bias of input_transform (cotracker3_offline.py:196)
-  RUN(launch_row_bias(time_emb, reinterpret_cast<const float*>(pk + L.win_f32), T, W.row_bias, R.s));
+  RUNC(CAT_MISC, launch_row_bias(time_emb, reinterpret_cast<const float*>(pk + L.win_f32), T, W.row_bias, R.s));
 
   for (int it = 0; it < iters; ++it) {
     // (i)+(ii) sampling + 4-D correlation, all levels -> split volume
-    RUN(launch_corr_sample(pyr, H4, W4, support, track_valid, coords, T, N, W.vol, g_opt_corr, num_sms(), R.s));
+    RUNC(CAT_CORR, launch_corr_sample(pyr, H4, W4, support, track_valid, coords, T, N, W.vol, g_opt_corr, num_sms(), R.s));
     // (iii) corr_mlp: 2401 -> 384 (GELU erf) -> 256, written straight into X columns [256*l, 256*l+256)
-    RUN(R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
+    RUNC(-1, R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
     {
       GemmEpilogue e = Runner::to_split(W.xs, 2 * kXPad, kXPad, 0);
       e.row_group = kL;
-      RUN(R.gemm(W.h1, L.corr_fc2, Mc, e));
+      RUNC(-1, R.gemm(W.h1, L.corr_fc2, Mc, e));
     }
     // vis, conf, posenc(rel. motion), zero pad -> X columns [1024,1152)
-    RUN(launch_build_x_small(coords, vis, conf, T, N, W.xs, R.s));
+    RUNC(CAT_MISC, launch_build_x_small(coords, vis, conf, T, N, W.xs, R.s));
     // input_transform (+ folded time embedding) -> point tokens
     {
       GemmEpilogue e = Runner::to_f32(W.tokens, kC, false);
       e.row_bias = W.row_bias;
       e.row_mod = T;
-      RUN(R.gemm(W.xs, L.in_tr, Rp, e));
+      RUNC(-1, R.gemm(W.xs, L.in_tr, Rp, e));
     }
     if (int rc = transformer_body(R, W, T, N)) return rc;
     // (v) heads + state update
-    RUN(launch_heads(W.tokens, reinterpret_cast<const float*>(pk + L.heads_w),
+    RUNC(CAT_MISC, launch_heads(W.tokens, reinterpret_cast<const float*>(pk + L.heads_w),
                      reinterpret_cast<const float*>(pk + L.heads_b), coords, vis, conf, nullptr, T, N, R.s));
   }
   return 0;
@@ -545,10 +586,10 @@ int ct3_updateformer(const void* packed, const float* x, int T, int N, float* de
   const Layout& L = layout();
   Runner R{reinterpret_cast<const uint8_t*>(packed), L, (cudaStream_t)stream, g_opt_gemm};
   const int Rp = N * T;
-  RUN(launch_split_rows(x, Rp, kX, kXPad, /*perm_x*/ 1, W.xs, 0, R.s));
-  RUN(R.gemm(W.xs, L.in_tr, Rp, Runner::to_f32(W.tokens, kC, false)));
+  RUNC(CAT_MISC, launch_split_rows(x, Rp, kX, kXPad, /*perm_x*/ 1, W.xs, 0, R.s));
+  RUNC(-1, R.gemm(W.xs, L.in_tr, Rp, Runner::to_f32(W.tokens, kC, false)));
   if (int rc = transformer_body(R, W, T, N)) return rc;
-  RUN(launch_heads(W.tokens, reinterpret_cast<const float*>(R.pk + L.heads_w),
+  RUNC(CAT_MISC, launch_heads(W.tokens, reinterpret_cast<const float*>(R.pk + L.heads_w),
                    reinterpret_cast<const float*>(R.pk + L.heads_b), nullptr, nullptr, nullptr, delta, T, N, R.s));
   return 0;
 }

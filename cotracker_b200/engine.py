@@ -48,6 +48,8 @@ def _declare(lib):
         "ct3_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_split_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_updateformer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "ct3_profile_enable": (c_int, [c_int]),
+        "ct3_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), intp, ctypes.POINTER(ctypes.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud
@@ -60,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "ct3_version", "ct3_last_error", "ct3_set_option", "ct3_get_option", "ct3_num_weight_tensors",
     "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
     "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
-    "ct3_corr_sample", "ct3_linear", "ct3_split_rows", "ct3_updateformer",
+    "ct3_corr_sample", "ct3_linear", "ct3_split_rows", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
 ]
 
 
@@ -270,3 +272,19 @@ def updateformer(packed, x: torch.Tensor, workspace: Optional[torch.Tensor] = No
         _check(lib().ct3_updateformer(_ptr(packed), _ptr(x), T, N, _ptr(delta), _ptr(workspace), workspace.numel(),
                                       _stream(x.device)), "ct3_updateformer")
     return delta
+
+
+PROFILE_CATEGORIES = ["corr_sample", "gemm", "attention", "layernorm", "misc"]
+
+
+def profile_enable(on: bool):
+    _check(lib().ct3_profile_enable(1 if on else 0), "ct3_profile_enable")
+
+
+def profile_read():
+    """-> ({category: ms}, {category: launches}, gemm_flops) accumulated since profile_enable(True)."""
+    ms = (ctypes.c_double * 5)()
+    n = (ctypes.c_int * 5)()
+    fl = ctypes.c_double(0)
+    _check(lib().ct3_profile_read(ms, n, ctypes.byref(fl)), "ct3_profile_read")
+    return dict(zip(PROFILE_CATEGORIES, list(ms))), dict(zip(PROFILE_CATEGORIES, list(n))), fl.value

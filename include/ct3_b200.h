@@ -125,6 +125,12 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
                     const float* time_emb, int T, int N, int iters, void* workspace,
                     size_t workspace_bytes, ct3_stream_t stream);
 
+/* ---- live profiler (bench.py roofline): CUDA events around every launch of the library, summed per
+ * kernel category: 0 corr_sample, 1 gemm (tcgen05), 2 attention, 3 layernorm, 4 misc.
+ * ct3_profile_enable(1) clears and starts recording; ct3_profile_read synchronises and sums. */
+int ct3_profile_enable(int on);
+int ct3_profile_read(double ms[5], int launches[5], double* gemm_flops);
+
 /* ---- stage-level entry points (used by the parity tests and profiles) ------- */
 
 /* Correlation sampling alone (get_correlation_feat + einsum,

@@ -158,7 +158,9 @@ def test_corr_mlp_gelu_variant_is_erf(eng):
         h_tanh = torch.nn.functional.gelu(torch.nn.functional.linear(vol, sd["corr_mlp.fc1.weight"], sd["corr_mlp.fc1.bias"]), approximate="tanh")
     assert float((h_erf - h_tanh).abs().max()) > 1e-4
     got = eng.linear(vol.to(DEV), sd["corr_mlp.fc1.weight"].to(DEV), sd["corr_mlp.fc1.bias"].to(DEV), act=1).cpu()
-    assert float((got - h_erf).abs().max()) < 0.2 * float((h_erf - h_tanh).abs().max())
+    # mean abs distance: GEMM rounding (~1e-5) is far below the erf/tanh gap (~2e-4)
+    d_erf, d_tanh = float((got - h_erf).abs().mean()), float((got - h_tanh).abs().mean())
+    assert d_erf < 0.2 * d_tanh, (d_erf, d_tanh)
 
 
 @pytest.mark.parametrize("impl", [0, 1])

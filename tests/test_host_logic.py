@@ -1,0 +1,123 @@
+"""CPU tests of the host side: ABI surface, state-dict contract, query construction, replica sharding (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cotracker_b200 import engine
+    lib = engine.lib()  # raises if the .so is missing: build it first (__graft_entry__.build)
+    header = open(os.path.join(ROOT, "include", "ct3_b200.h")).read()
+    declared = set(re.findall(r"\b(ct3_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ct3_update_iter"}  # mentioned in a comment only
+    assert declared == set(engine.EXPORTED_SYMBOLS), declared ^ set(engine.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ct3_version() >= 100
+
+
+def test_abi_argument_validation_without_gpu():
+    from cotracker_b200 import engine
+    lib = engine.lib()
+    n = ctypes.c_size_t(0)
+    assert lib.ct3_workspace_bytes(16, 6400, ctypes.byref(n)) == 0 and n.value > 6e9
+    assert lib.ct3_workspace_bytes(0, 10, ctypes.byref(n)) == -1          # CT3_EINVAL
+    assert b"T and N" in lib.ct3_last_error()
+    assert lib.ct3_workspace_bytes(4, 4, None) == -1
+    off, h, w, total = engine.pyramid_layout(16, 96, 128)
+    assert h == [96, 48, 24, 12] and w == [128, 64, 32, 16] and total == 16 * 16320 * 128
+    with pytest.raises(engine.EngineError):
+        engine.pyramid_layout(2, 4, 4)                                      # level 3 would be 0x0
+    assert lib.ct3_set_option(b"nope", 1) == -1
+    assert engine.get_option("gemm") == 0
+    assert lib.ct3_update_loop(None, None, 1, 1, None, None, None, None, None, None, 1, 1, 1, None, 0, None) == -1
+
+
+def test_weight_names_match_state_dict():
+    from cotracker_b200 import engine
+    from cotracker_b200.build import build_cotracker
+    names = engine.weight_names()
+    sd = build_cotracker(None, offline=True, window_len=60).state_dict()
+    hot = [k for k in sd if k.startswith(("updateformer.", "corr_mlp."))]
+    assert sorted(names) == sorted(hot)
+    assert len(names) == 143
+    assert sum(sd[k].numel() for k in sd if k != "time_emb") == 25385700
+    assert sd["time_emb"].shape == (1, 60, 1110)
+    assert "updateformer.virual_tracks" in sd                                   # (sic)
+
+
+def test_v2_and_training_are_rejected():
+    from cotracker_b200.build import build_cotracker
+    with pytest.raises(NotImplementedError):
+        build_cotracker(None, v2=True)
+
+
+def test_grid_queries_match_reference_contract():
+    from cotracker_b200.predictor import get_points_on_a_grid
+    g = get_points_on_a_grid(80, (384, 512))
+    assert g.shape == (1, 6400, 2)
+    assert float(g[0, :, 0].min()) == 8.0 and float(g[0, :, 0].max()) == 504.0   # margin W/64
+    assert float(g[0, :, 1].min()) == 8.0 and float(g[0, :, 1].max()) == 376.0
+    assert torch.equal(g[0, 1] - g[0, 0], torch.tensor([g[0, 1, 0] - 8.0, 0.0]))     # row-major, x fastest
+    assert get_points_on_a_grid(1, (384, 512)).tolist() == [[[256.0, 192.0]]]
+
+
+def test_grid_and_time_embedding_match_live_reference(reference_path):
+    sys.path.insert(0, reference_path)
+    from cotracker.models.core.model_utils import get_points_on_a_grid as ref_grid
+    from cotracker.models.core.embeddings import get_1d_sincos_pos_embed_from_grid
+    from cotracker_b200.model import sincos_time_embedding
+    from cotracker_b200.predictor import get_points_on_a_grid
+    for size in (1, 5, 30):
+        assert torch.equal(get_points_on_a_grid(size, (384, 512)), ref_grid(size, (384, 512)))
+    for L in (16, 60):
+        ref = get_1d_sincos_pos_embed_from_grid(1110, torch.linspace(0, L - 1, L).reshape(1, L, 1)[0])
+        assert torch.equal(sincos_time_embedding(1110, L), ref)
+
+
+def test_shard_clips():
+    from cotracker_b200.sharding import shard_clips
+    assert [shard_clips(8, 8, r) for r in range(8)] == [[r] for r in range(8)]
+    assert shard_clips(10, 4, 1) == [1, 5, 9]
+    assert sorted(sum((shard_clips(13, 4, r) for r in range(4)), [])) == list(range(13))
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from cotracker_b200.build import build_cotracker
+from cotracker_b200.sharding import broadcast_state_dict, shard_clips, gather_results
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(100 + rank)                      # different random weights per rank before the broadcast
+m = build_cotracker(None, offline=False, window_len=16)
+sent = broadcast_state_dict(m, src=0)
+ref = torch.cat([v.reshape(-1).float() for _, v in sorted(m.state_dict().items())])
+chk = ref.clone(); dist.broadcast(chk, src=0)
+assert torch.equal(ref, chk), "weights differ after broadcast"
+assert sent >= 25385700 * 4
+mine = shard_clips(5, world, rank)
+tr = torch.full((1, 2, 3, 2), float(rank)); vi = torch.ones(1, 2, 3, dtype=torch.bool)
+tl, vl = gather_results(tr, vi, dst=0)
+if rank == 0:
+    assert [float(t.mean()) for t in tl] == [0.0, 1.0] and all(v.all() for v in vl)
+print("OK", rank, mine)
+"""
+
+
+def test_replica_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK 0 [0, 2, 4]" in r.stdout and "OK 1 [1, 3]" in r.stdout
