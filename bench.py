@@ -44,6 +44,24 @@ def peaks():
     return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, source="fallback")
 
 
+
+def usable_cores() -> int:
+    """CPU threads this process may actually use: affinity mask and cgroup quota, not the host's core count
+    (oversubscribing OpenMP threads in a CPU-limited container is catastrophically slow)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 64))
+
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -105,7 +123,7 @@ def bench_reference(args, rank):
     from cotracker_b200.synthetic import seeded_state_dict, texture_video
     from oracle import ct3_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     total = args.steps + args.warmup
     # cost model measured on the build box (8 threads): ~3.5 s encoder + 18.5 ms per track; bound the whole run to ~3 min
@@ -269,7 +287,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded CPU sample of the same workload through the oracle port (reported baseline, not the target)
         from oracle import ct3_oracle as O
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         torch.set_num_threads(cores)
         g = 20
         sd_cpu = seeded_state_dict(1234, offline=True, window_len=60)
