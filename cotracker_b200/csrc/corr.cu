@@ -124,9 +124,8 @@ corr_sample_simt_kernel(CorrArgs g) {
 cudaError_t launch_corr_sample(const float* pyr, int H4, int W4, const float* support,
                                const uint8_t* track_valid, const float* coords, int T, int N,
                                __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s) {
-  (void)impl;
-  (void)num_sms;
-  CorrArgs g;
+  if (impl == 0) return launch_corr_sample_tc(pyr, H4, W4, support, track_valid, coords, T, N, vol_split, num_sms, s);
+  CorrArgs g;  // impl 1: exact-fp32 SIMT verification kernel
   g.pyr = pyr;
   g.lay = pyramid_layout(T, H4, W4);
   g.support = support;

@@ -22,6 +22,10 @@ cudaError_t launch_corr_sample(const float* pyr, int H4, int W4, const float* su
                                const uint8_t* track_valid, const float* coords, int T, int N,
                                __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s);
 
+cudaError_t launch_corr_sample_tc(const float* pyr, int H4, int W4, const float* support,
+                                  const uint8_t* track_valid, const float* coords, int T, int N,
+                                  __nv_bfloat16* vol_split, int num_sms, cudaStream_t s);
+
 // ---- tokens.cu : elementwise / row-wise pieces of the transformer ---------------------------------
 cudaError_t launch_layernorm_split(const float* x, int rows, const float* gamma, const float* beta, float eps,
                                    __nv_bfloat16* out_split, cudaStream_t s);
