@@ -12,17 +12,18 @@
 //   D       [128 x  64] : fp32 in TMEM, 3 tcgen05.mma per k16 step (lo*hi + hi*lo + hi*hi), double buffered
 //   epilogue            : tcgen05.ld -> split-bf16 -> staging image of the complete 9728-byte volume rows
 //                         ([hi(2432) | lo(2432)], K padding zero) -> fully coalesced 16-byte stores
-// Warps: 0..6 producers (warp w owns x-offset a = w), 7 = TMEM alloc + MMA issuer, 8..11 epilogue.
+// Warps: 0..13 producers (warp w owns frame w/7 and x-offset a = w%7 of the tile; all 16 tap loads of a column
+// are issued before the first use), 14 = TMEM alloc + MMA issuer, 15..18 epilogue.
 // Neither the sampled features (10 GB/iteration in the reference) nor an fp32 volume ever touch HBM.
 #include "kernels.cuh"
 
 namespace ct3 {
 namespace {
 
-constexpr int PW = 7;                     // producer warps
-constexpr int MMA_WARP = 7;
-constexpr int EPI_WARP0 = 8;
-constexpr int THREADS = 12 * 32;
+constexpr int PW = 14;                    // producer warps: warp w -> (frame w/7 of the tile, x-offset a = w%7)
+constexpr int MMA_WARP = 14;
+constexpr int EPI_WARP0 = 15;             // warps 15..18 cover the four TMEM lane quarters (warp & 3)
+constexpr int THREADS = 19 * 32;
 constexpr int A_PART = 2 * 16384;         // one bf16 plane of A: 2 K-atoms x [128 rows x 128 B]
 constexpr int A_STAGE = 2 * A_PART;       // hi + lo = 64 KiB
 constexpr int S_PART = 2 * 8192;          // one plane of S: 2 K-atoms x [64 rows x 128 B]
@@ -109,7 +110,7 @@ corr_sample_tc_kernel(CorrTcArgs g, int num_units) {
   if (warp < PW) {
     // ================================================================== producers
     const LanePos lp = lane_pos(lane);
-    const int a = warp;  // x-offset index owned by this warp
+    const int f = warp / 7, a = warp % 7;  // frame of the tile / x-offset index owned by this warp
     uint32_t it = 0;     // tile counter of this CTA
     uint32_t ui = 0;     // unit counter of this CTA
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
@@ -131,48 +132,62 @@ corr_sample_tc_kernel(CorrTcArgs g, int num_units) {
         __syncwarp();
         if (lane == 0) mbar_arrive(s_full);
       }
-      // ---- A tiles: two frames each
+      // ---- A tiles: two frames each, one (frame, x-offset) column of 7 samples per warp
       for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
         const int stage = it & 1;
-        mbar_wait(&a_empty[stage], ((it >> 1) & 1u) ^ 1u);
-        uint8_t* a_hi = smem + OFF_A + stage * A_STAGE;
-        uint8_t* a_lo = a_hi + A_PART;
-#pragma unroll 1
-        for (int f = 0; f < 2; ++f) {
-          const int t = 2 * tp + f;
-          if (t >= g.T) break;
+        const int t = 2 * tp + f;
+        // addresses and weights first (independent of the smem slot) ...
+        float wy[7];
+        int y0[7], yl[8];   // yl[0] = y0 of sample 0, yl[k+1] = y1 of sample k: the (<= 8) distinct rows of the column
+        float4 hrow[8];
+        const float* fm = g.pyr + g.lay.off[l] + (int64_t)min(t, g.T - 1) * H * W * kD;
+        int x0 = 0, x1 = 0;
+        float wx = 0.f;
+        if (t < g.T) {
           const float cx = g.coords[((int64_t)t * g.N + n) * 2 + 0] * inv;
           const float cy = g.coords[((int64_t)t * g.N + n) * 2 + 1] * inv;
-          const float* fm = g.pyr + g.lay.off[l] + (int64_t)t * H * W * kD;
           const float x = fminf(fmaxf(cx + (float)(a - kR), 0.f), (float)(W - 1));
           const float xf = floorf(x);
-          const int x0 = (int)xf, x1 = min(x0 + 1, W - 1);
-          const float wx = x - xf;
-          int prev_y1 = -1;
-          float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          x0 = (int)xf;
+          x1 = min(x0 + 1, W - 1);
+          wx = x - xf;
 #pragma unroll
           for (int b = 0; b < 7; ++b) {
             const float y = fminf(fmaxf(cy + (float)(b - kR), 0.f), (float)(H - 1));
             const float yf = floorf(y);
-            const int y0 = (int)yf, y1 = min(y0 + 1, H - 1);
-            const float wy = y - yf;
+            y0[b] = (int)yf;
+            wy[b] = y - yf;
+            if (b == 0) yl[0] = y0[0];
+            yl[b + 1] = min(y0[b] + 1, H - 1);
+          }
+          // ... then all 16 taps in flight at once (one L2 round trip per column instead of eight)
+          float4 p0[8], p1[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            p0[k] = __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)yl[k] * W + x0) * kD) + lane);
+            p1[k] = __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)yl[k] * W + x1) * kD) + lane);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hrow[k] = lerp4(p0[k], p1[k], wx);
+        }
+        mbar_wait(&a_empty[stage], ((it >> 1) & 1u) ^ 1u);
+        if (t < g.T) {
+          uint8_t* a_hi = smem + OFF_A + stage * A_STAGE;
+          uint8_t* a_lo = a_hi + A_PART;
+#pragma unroll
+          for (int b = 0; b < 7; ++b) {
+            // rows are consecutive unless the sample was clamped at the low border (y0 stays at row yl[0]); a
+            // floor() jump caused by fp32 rounding of cy + offset (probability ~1e-7) takes the direct path
             float4 h0;
-            if (y0 == prev_y1) {
-              h0 = h1;  // row shared with the previous sample (always, unless clamped)
+            if (y0[b] == yl[b]) {
+              h0 = hrow[b];
+            } else if (y0[b] == yl[0]) {
+              h0 = hrow[0];
             } else {
-              const float4 p0 = __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y0 * W + x0) * kD) + lane);
-              const float4 p1 = __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y0 * W + x1) * kD) + lane);
-              h0 = lerp4(p0, p1, wx);
+              h0 = lerp4(__ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y0[b] * W + x0) * kD) + lane),
+                         __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y0[b] * W + x1) * kD) + lane), wx);
             }
-            if (y1 == y0) {
-              h1 = h0;
-            } else {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y1 * W + x0) * kD) + lane);
-              const float4 q1 = __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y1 * W + x1) * kD) + lane);
-              h1 = lerp4(q0, q1, wx);
-            }
-            prev_y1 = y1;
-            store_split4(a_hi, a_lo, 16384, f * kP + a * 7 + b, lp, lerp4(h0, h1, wy));
+            store_split4(a_hi, a_lo, 16384, f * kP + a * 7 + b, lp, lerp4(h0, hrow[b + 1], wy[b]));
           }
         }
         fence_proxy_async_smem();
