@@ -16,7 +16,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 int g_opt_gemm = 0;  // 0 tcgen05, 1 SIMT verification
-int g_opt_corr = 0;  // reserved for correlation kernel variants
+int g_opt_corr = 0;  // 0 tcgen05 fused kernel, 1 SIMT verification
+int g_opt_attn = 0;  // 0 tensor-core flash kernel, 1 SIMT verification
 
 int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -171,6 +172,7 @@ struct Workspace {
   float* vqkv;            // [64*T, 1152]       (virtual q / kv / qkv)
   __nv_bfloat16* hmid;    // [(N+64)*T, 2*1536]
   float* row_bias;        // [T, 384]
+  float* att_part;        // split-K partials of the virtual<-point attention
   size_t total;
 };
 Workspace carve(void* base, int T, int N) {
@@ -189,6 +191,7 @@ Workspace carve(void* base, int T, int N) {
   w.vqkv = (float*)take(Rv * 3 * kC * 4);
   w.hmid = (__nv_bfloat16*)take(R * 2 * kMlpHid * 2);
   w.row_bias = (float*)take((size_t)T * kC * 4);
+  w.att_part = (float*)take(attention_partial_bytes(T, kV, kAttnMaxSplits));
   w.total = off;
   return w;
 }
@@ -237,6 +240,11 @@ struct Runner {
     }                                                                                    \
   } while (0)
 
+int run_attention(Runner& R, const Workspace& W, const AttnParams& a, bool per_warp) {
+  if (g_opt_attn == 1) return (int)launch_attention(a, R.s);
+  return (int)launch_attention_tc(a, per_warp, W.att_part, num_sms(), R.s);
+}
+
 // x += to_out(attn(...)); x += mlp(LN(x))   for the rows [row0, row0+rows) of the token buffer
 int mlp_half(Runner& R, const Workspace& W, const Block& b, int64_t row0, int rows) {
   float* x = W.tokens + row0 * kC;
@@ -273,7 +281,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = N + kV; a.Lq = T; a.Lk = T;
       a.q_seq_stride = T; a.q_tok_stride = 1; a.k_seq_stride = T; a.k_tok_stride = 1;
       a.scale = scale;
-      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(CAT_ATTN, run_attention(R, W, a, true));
       RUNC(-1, R.gemm(W.att, b.out, Rall, Runner::to_f32(W.tokens, kC, true)));
       if (int rc = mlp_half(R, W, b, 0, Rall)) return rc;
     }
@@ -291,7 +299,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = T; a.Lq = kV; a.Lk = N;
       a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
       a.scale = scale;
-      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(CAT_ATTN, run_attention(R, W, a, false));
       RUNC(-1, R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
       if (int rc = mlp_half(R, W, b, Rp, Rv)) return rc;
     }
@@ -306,7 +314,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = T; a.Lq = kV; a.Lk = kV;
       a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
       a.scale = scale;
-      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(CAT_ATTN, run_attention(R, W, a, false));
       RUNC(-1, R.gemm(att_v, b.out, Rv, Runner::to_f32(vtok, kC, true)));
       if (int rc = mlp_half(R, W, b, Rp, Rv)) return rc;
     }
@@ -324,7 +332,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       a.num_seq = T; a.Lq = N; a.Lk = kV;
       a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
       a.scale = scale;
-      RUNC(CAT_ATTN, launch_attention(a, R.s));
+      RUNC(CAT_ATTN, run_attention(R, W, a, false));
       RUNC(-1, R.gemm(att_p, b.out, Rp, Runner::to_f32(W.tokens, kC, true)));
       if (int rc = mlp_half(R, W, b, 0, Rp)) return rc;
     }
@@ -350,12 +358,14 @@ int ct3_set_option(const char* name, int value) {
   if (!name) return fail(CT3_EINVAL, "null option name%s");
   if (!strcmp(name, "gemm")) { if (value < 0 || value > 1) return fail(CT3_EINVAL, "gemm option must be 0 or 1%s"); g_opt_gemm = value; return 0; }
   if (!strcmp(name, "corr")) { g_opt_corr = value; return 0; }
+  if (!strcmp(name, "attn")) { g_opt_attn = value; return 0; }
   return fail(CT3_EINVAL, "unknown option %s", name);
 }
 int ct3_get_option(const char* name, int* value) {
   if (!name || !value) return fail(CT3_EINVAL, "null argument%s");
   if (!strcmp(name, "gemm")) { *value = g_opt_gemm; return 0; }
   if (!strcmp(name, "corr")) { *value = g_opt_corr; return 0; }
+  if (!strcmp(name, "attn")) { *value = g_opt_attn; return 0; }
   return fail(CT3_EINVAL, "unknown option %s", name);
 }
 

@@ -50,6 +50,11 @@ struct AttnParams {
   int64_t k_seq_stride, k_tok_stride;  // k/v row  = s*k_seq_stride + j*k_tok_stride
   float scale;
 };
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);   // exact-fp32 SIMT (verification)
+
+// ---- attention_tc.cu : tensor-core (mma.sync split-bf16x3) production path ------------------------
+constexpr int kAttnMaxSplits = 32;
+size_t attention_partial_bytes(int num_seq, int Lq, int max_splits);
+cudaError_t launch_attention_tc(const AttnParams& p, bool per_warp, float* part, int num_sms, cudaStream_t s);
 
 }  // namespace ct3

@@ -154,6 +154,27 @@ def test_updateformer_stage(eng, impl):
     assert err < 2e-4 * max(scale, 1.0), (err, scale)
 
 
+@pytest.mark.parametrize("attn", [0, 1])   # 0: tensor-core flash kernel (product), 1: exact-fp32 SIMT cross-check
+@pytest.mark.parametrize("N,T", [(70, 6), (600, 20), (130, 40), (1030, 16)])
+def test_updateformer_attention_shapes(eng, attn, N, T):
+    """Exercises every attention variant: per-warp time attention with KB=16/32/64, shared K/V, split-K + combine
+    (N >= 512 keys), ragged query/key tails."""
+    sd = _amplified_sd(seed=3, head_gain=100.0, vis_gain=100.0)
+    g = torch.Generator().manual_seed(N + T)
+    x = torch.randn(N, T, 1110, generator=g)
+    with torch.no_grad():
+        want = O.updateformer(sd, x[None])[0]
+    packed = eng.pack_weights(sd, DEV)
+    eng.set_option("attn", attn)
+    try:
+        got = eng.updateformer(packed, x.to(DEV)).cpu()
+    finally:
+        eng.set_option("attn", 0)
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max())
+    assert err < 2e-4 * max(scale, 1.0), (attn, N, T, err, scale)
+
+
 def test_corr_mlp_gelu_variant_is_erf(eng):
     """Mutation guard: with volume x10 the erf and tanh GELUs differ by >1e-3."""
     sd = _amplified_sd()
