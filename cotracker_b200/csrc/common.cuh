@@ -65,9 +65,11 @@ __device__ __forceinline__ float gelu_erf(float x) {   // nn.GELU() (blocks.py:4
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float gelu_tanh(float x) {  // nn.GELU(approximate="tanh") (blocks.py:418)
+  // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + exp(-2u)),  u = sqrt(2/pi) (x + 0.044715 x^3).
+  // ex2.approx + rcp.approx: ~1e-6 relative (tanh.approx would be 5e-4) at 1/5 of the instructions of tanhf.
   const float k0 = 0.79788456080286535588f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float u = k0 * (x + k1 * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -3,7 +3,7 @@
 // Persistent warp-specialised kernel, one CTA per SM:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 3-stage ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per k16 step: hi*hi, lo*hi, hi*lo)
-//   warps 2..5  : epilogue       (tcgen05.ld -> bias / row-bias / GELU / residual -> fp32 and/or split-bf16 stores)
+//   warps 2..9  : epilogue       (tcgen05.ld -> bias / row-bias / GELU / residual -> fp32 and/or split-bf16 stores)
 // Two 128-column fp32 accumulators in TMEM are double buffered so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Tiles are 128 x 128; consecutive tile ids share the X (activation) tile so the
 // big operand is read from HBM once and hit in L2 by the CTAs working on its other N-tiles.
@@ -21,7 +21,8 @@ constexpr int TILE_A = BM * BK * 2;                    // 16 KiB (bf16)
 constexpr int TILE_B = BN * BK * 2;                    // 16 KiB
 constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;   // hi+lo of both operands = 64 KiB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                           // two warps per TMEM lane quarter, half the columns each
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr uint32_t TMEM_COLS = ACC * BN;               // 256 columns (power of two)
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -103,7 +104,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
     for (int i = 0; i < ACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -170,7 +171,8 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (warps 2,3,4,5 -> 2,3,0,1)
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warp id % 4)
+    const int chunk0 = ((warp - 2) >> 2) * (BN / 64);  // warps 2..5: columns [0,64), warps 6..9: [64,128)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -179,7 +181,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       tc_fence_after_sync();
       const int row = mt * BM + quarter * 32 + lane;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
         float v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32);
         tmem_ld32(taddr, v);
