@@ -20,8 +20,12 @@ constexpr int STAGES = 3, ACC = 2;
 constexpr int TILE_A = BM * BK * 2;                    // 16 KiB (bf16)
 constexpr int TILE_B = BN * BK * 2;                    // 16 KiB
 constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;   // hi+lo of both operands = 64 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int EPI_WARPS = 8;                           // two warps per TMEM lane quarter, half the columns each
+constexpr int STG_WORDS = 32 * 33;                     // per-warp transpose buffer (padded: conflict-free both ways)
+constexpr int OFF_STG = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_WORDS * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 128 /*barriers*/ + 1024 /*align slack*/;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr uint32_t TMEM_COLS = ACC * BN;               // 256 columns (power of two)
 
@@ -31,8 +35,14 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// one thread = one output row, 32 consecutive columns starting at col0
-__device__ __forceinline__ void epilogue_store32(const GemmEpilogue& e, int N, int row, int col0, float (&v)[32]) {
+// Epilogue of one 32-row x 32-column chunk by one warp.  Phase 1 (lane = row, straight out of tcgen05.ld):
+// bias / row-bias / activation, then the 32 output words of the row (fp32, or 16 packed-hi | 16 packed-lo bf16
+// pairs) go to a padded (stride 33) per-warp staging buffer.  Phase 2 (lane = word): every global access of the
+// warp is one contiguous 128-byte (fp32) or 2 x 64-byte (split planes) row segment -- 8x fewer LSU wavefronts
+// than letting each thread stream its own row.
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int N, int row0, int col0, int lane,
+                                               float (&v)[32], uint32_t* stg) {
+  const int row = row0 + lane;
   if (e.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
@@ -41,7 +51,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue& e, int N, i
       v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
   }
-  if (e.row_bias) {
+  if (e.row_bias && row < M) {
     const float4* b4 = reinterpret_cast<const float4*>(e.row_bias + (int64_t)(row % e.row_mod) * N + col0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -54,31 +64,45 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue& e, int N, i
     for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
   }
   if (e.out_f32) {
-    float4* o4 = reinterpret_cast<float4*>(e.out_f32 + (int64_t)row * e.ld_f32 + col0);
-    if (e.residual) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __float_as_uint(v[c]);
+    __syncwarp();
+    float* base = e.out_f32 + (int64_t)row0 * e.ld_f32 + col0 + lane;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      float x[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float4 r = o4[i];
-        v[4 * i + 0] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
+        x[i] = __uint_as_float(stg[(r0 + i) * 33 + lane]);
+        if (e.residual && row0 + r0 + i < M) x[i] += base[(int64_t)(r0 + i) * e.ld_f32];
       }
-    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int i = 0; i < 8; ++i)
+        if (row0 + r0 + i < M) base[(int64_t)(r0 + i) * e.ld_f32] = x[i];
+    }
+    __syncwarp();
   }
   if (e.out_split) {
-    const int orow = row / e.row_group;
-    const int ocol = (row % e.row_group) * N + col0;
-    __nv_bfloat16* hp = e.out_split + (int64_t)orow * e.ld_split + ocol;
-    uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-    uint4* h4 = reinterpret_cast<uint4*>(hp);
-    uint4* l4 = reinterpret_cast<uint4*>(hp + e.lo_off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-      l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    for (int i = 0; i < 16; ++i) {
+      uint32_t hi, lo;
+      split2(v[2 * i], v[2 * i + 1], hi, lo);
+      stg[lane * 33 + i] = hi;
+      stg[lane * 33 + 16 + i] = lo;
     }
+    __syncwarp();
+    const int half = lane >> 4, w = lane & 15;   // lanes 0..15: hi plane, 16..31: lo plane
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const int grow = row0 + r;
+      if (grow < M) {
+        const int orow = grow / e.row_group;
+        const int ocol = (grow % e.row_group) * N + col0;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(e.out_split + (int64_t)orow * e.ld_split + ocol + half * e.lo_off);
+        dst[w] = stg[r * 33 + lane];
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -87,7 +111,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                       int N, int Kpad, GemmEpilogue epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC;
@@ -179,13 +203,14 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const int mt = tile / num_nt, nt = tile % num_nt;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
-      const int row = mt * BM + quarter * 32 + lane;
+      const int row0 = mt * BM + quarter * 32;
+      uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
 #pragma unroll 1
       for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
         float v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32);
         tmem_ld32(taddr, v);
-        if (row < M) epilogue_store32(epi, N, row, nt * BN + chunk * 32, v);
+        epilogue_chunk(epi, M, N, row0, nt * BN + chunk * 32, lane, v, stg);
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty_bar[acc]);
