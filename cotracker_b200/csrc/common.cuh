@@ -54,11 +54,13 @@ __device__ __forceinline__ bf16pair split_bf16(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
-// split 2 floats -> packed hi pair, packed lo pair
+// split 2 floats -> packed hi pair, packed lo pair (a in the low half); cvt.rn.bf16x2.f32 does both lanes at once
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  bf16pair pa = split_bf16(a), pb = split_bf16(b);
-  hi = pack_bf16x2(pa.hi, pb.hi);
-  lo = pack_bf16x2(pa.lo, pb.lo);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {   // nn.GELU() (blocks.py:48)

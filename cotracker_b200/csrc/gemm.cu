@@ -68,18 +68,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
     for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __float_as_uint(v[c]);
     __syncwarp();
     float* base = e.out_f32 + (int64_t)row0 * e.ld_f32 + col0 + lane;
-#pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-      float x[8];
+    const int nrow = min(32, M - row0);   // warp-uniform
+    float x[32];
+    if (e.residual) {
+      // all residual rows in flight at once (v[] is dead: its registers are reused)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x[i] = __uint_as_float(stg[(r0 + i) * 33 + lane]);
-        if (e.residual && row0 + r0 + i < M) x[i] += base[(int64_t)(r0 + i) * e.ld_f32];
-      }
+      for (int r = 0; r < 32; ++r) x[r] = r < nrow ? base[(int64_t)r * e.ld_f32] : 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (row0 + r0 + i < M) base[(int64_t)(r0 + i) * e.ld_f32] = x[i];
+      for (int r = 0; r < 32; ++r) x[r] += __uint_as_float(stg[r * 33 + lane]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) x[r] = __uint_as_float(stg[r * 33 + lane]);
     }
+#pragma unroll
+    for (int r = 0; r < 32; ++r)
+      if (r < nrow) base[(int64_t)r * e.ld_f32] = x[r];
     __syncwarp();
   }
   if (e.out_split) {
@@ -91,16 +94,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
       stg[lane * 33 + 16 + i] = lo;
     }
     __syncwarp();
+    // element offset of this lane's row (one division per chunk); broadcast per row with a shuffle below
+    long long off_lane = -1;
+    if (row < M) {
+      const int orow = row / e.row_group;
+      off_lane = (long long)orow * e.ld_split + (long long)(row % e.row_group) * N + col0;
+    }
     const int half = lane >> 4, w = lane & 15;   // lanes 0..15: hi plane, 16..31: lo plane
-#pragma unroll 4
+#pragma unroll
     for (int r = 0; r < 32; ++r) {
-      const int grow = row0 + r;
-      if (grow < M) {
-        const int orow = grow / e.row_group;
-        const int ocol = (grow % e.row_group) * N + col0;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(e.out_split + (int64_t)orow * e.ld_split + ocol + half * e.lo_off);
-        dst[w] = stg[r * 33 + lane];
-      }
+      const long long off = __shfl_sync(0xffffffffu, off_lane, r);
+      if (off >= 0) reinterpret_cast<uint32_t*>(e.out_split + off + half * e.lo_off)[w] = stg[r * 33 + lane];
     }
     __syncwarp();
   }
