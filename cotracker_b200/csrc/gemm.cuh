@@ -34,6 +34,11 @@ struct GemmProblem {
   GemmEpilogue epi;
 };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
+// dims/box innermost first; strides_bytes has rank-1 entries (innermost stride is the element size).
+bool encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 // 0 = tcgen05 path, 1 = SIMT verification path.  Returns cudaError_t as int (0 = ok).
 int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream, const char** err);
 
