@@ -106,28 +106,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (wake-on-complete) or
+// the hint expires, instead of burning issue slots in a polling loop (same form as cutlass ClusterBarrier::wait).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must surface as a trap (-> cudaErrorLaunchFailure),
-// never as a hung GPU box.  2^28 polls of a HW-sleeping try_wait is >> any legal wait.
+// Bounded: a protocol bug must surface as a trap (-> cudaErrorLaunchFailure), never as a hung GPU box
+// (2^16 expirations of a 0.1 ms hint = seconds; every legal wait here is microseconds).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
-      asm volatile("trap;");
-    }
+    if (++spins > (1u << 16)) asm volatile("trap;");
   }
+}
+
+// Dynamic shared memory base rounded up to 1024 B WITHOUT leaving the shared address space (an integer round trip
+// through uintptr_t turns every later access into a generic LD/ST).
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
 }
 
 // ----------------------------------------------------------------------------------------------

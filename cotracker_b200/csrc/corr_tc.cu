@@ -91,8 +91,8 @@ __device__ __forceinline__ int box_origin(float c, int size) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int num_units) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* a_full = bars;          // samplers -> MMA            (count 14)
   uint64_t* a_empty = bars + 1;     // MMA -> samplers            (tcgen05.commit)

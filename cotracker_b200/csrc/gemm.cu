@@ -113,8 +113,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
                       int N, int Kpad, GemmEpilogue epi) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
