@@ -90,7 +90,7 @@ __device__ __forceinline__ int box_origin(float c, int size) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int num_units) {
+corr_sample_tc_kernel(const __grid_constant__ CorrTcArgs g, const __grid_constant__ CorrMaps maps, int num_units) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -132,9 +132,13 @@ corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int n
     const LanePos lp = lane_pos(lane);
     const int f = warp / 7, a = warp % 7;  // frame of the tile / x-offset index owned by this warp
     uint32_t it = 0, ui = 0, fc = 0;       // tile / unit / frame counters of this CTA
+    uint32_t aoff[7];                      // byte offsets of this lane's 8-byte slot in the 7 A rows it writes
+#pragma unroll
+    for (int b = 0; b < 7; ++b) aoff[b] = (uint32_t)(lp.atom * 16384) + sw128(f * kP + a * 7 + b, lp.chunk) + (uint32_t)(lp.half * 8);
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
       const int n = u / kL, l = u % kL;
       const int H = g.lay.h[l], W = g.lay.w[l];
+      const int bw = min(W, 8), bh = min(H, 8);        // box extent (maps narrower than 8 texels: whole map)
       // ---- support tile (B operand), once per unit
       if (ui > 0) mbar_wait(s_empty, (ui - 1) & 1u);   // MMAs of the previous unit have retired
       {
@@ -162,14 +166,11 @@ corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int n
           const float4 prm = *reinterpret_cast<const float4*>(smem + OFF_PARAM + slot * 16);
           const float cx = prm.x, cy = prm.y;
           const int bx = __float_as_int(prm.z), by = __float_as_int(prm.w);
-          const int bw = min(W, 8), bh = min(H, 8);    // box extent (maps narrower than 8 texels: whole map)
           const float* patch = reinterpret_cast<const float*>(smem + OFF_PATCH + slot * PATCH_BYTES) + lane * 4;
-          const float* fm = g.pyr + g.lay.off[l] + (int64_t)t * H * W * kD + lane * 4;
           const float x = fminf(fmaxf(cx + (float)(a - kR), 0.f), (float)(W - 1));
           const float xf = floorf(x);
           const int x0 = (int)xf, x1 = min(x0 + 1, W - 1);
           const float wx = x - xf;
-          const bool x_in = (x0 >= bx) && (x1 <= bx + bw - 1);
           float wy[7];
           int y0[7], yl[8];   // yl[0] = y0 of sample 0, yl[k+1] = y1 of sample k: the (<= 8) distinct rows of the column
 #pragma unroll
@@ -181,27 +182,39 @@ corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int n
             if (b == 0) yl[0] = y0[0];
             yl[b + 1] = min(y0[b] + 1, H - 1);
           }
-          // one blended texel row: from the staged patch (always, bar fp32 corner cases) or straight from global
-          auto hrow_at = [&](int yy) -> float4 {
-            if (x_in && yy >= by && yy <= by + bh - 1) {
-              const float* r = patch + ((yy - by) * bw - bx) * kD;
-              return lerp4(*reinterpret_cast<const float4*>(r + x0 * kD), *reinterpret_cast<const float4*>(r + x1 * kD), wx);
+          // fast path (always, bar fp32 corner cases of floor(c + offset)): every tap of the column is in the box
+          // and each sample's upper row is either the previous sample's lower row or (low-border clamp) row yl[0]
+          bool fast = (x0 >= bx) && (x1 < bx + bw) && (yl[0] >= by) && (yl[7] < by + bh);
+#pragma unroll
+          for (int b = 1; b < 7; ++b) fast = fast && ((y0[b] == yl[b]) || (y0[b] == yl[0]));
+          if (fast) {
+            const float* pa = patch + (x0 - bx) * kD;
+            const float* pb = patch + (x1 - bx) * kD;
+            float4 hrow[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int ro = (yl[k] - by) * bw * kD;
+              hrow[k] = lerp4(*reinterpret_cast<const float4*>(pa + ro), *reinterpret_cast<const float4*>(pb + ro), wx);
             }
-            return lerp4(__ldg(reinterpret_cast<const float4*>(fm + ((int64_t)yy * W + x0) * kD)),
-                         __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)yy * W + x1) * kD)), wx);
-          };
-          float4 hrow[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) hrow[k] = hrow_at(yl[k]);
+            for (int b = 0; b < 7; ++b) {
+              const bool same = (y0[b] == yl[b]);
+              float4 h0;
+              h0.x = same ? hrow[b].x : hrow[0].x; h0.y = same ? hrow[b].y : hrow[0].y;
+              h0.z = same ? hrow[b].z : hrow[0].z; h0.w = same ? hrow[b].w : hrow[0].w;
+              outv[b] = lerp4(h0, hrow[b + 1], wy[b]);
+            }
+          } else {
+            const float* fm = g.pyr + g.lay.off[l] + (int64_t)t * H * W * kD + lane * 4;
 #pragma unroll
-          for (int b = 0; b < 7; ++b) {
-            // rows are consecutive unless the sample was clamped at the low border (y0 stays at row yl[0]); a
-            // floor() jump caused by fp32 rounding of cy + offset (probability ~1e-7) takes the direct path
-            float4 h0;
-            if (y0[b] == yl[b]) h0 = hrow[b];
-            else if (y0[b] == yl[0]) h0 = hrow[0];
-            else h0 = hrow_at(y0[b]);
-            outv[b] = lerp4(h0, hrow[b + 1], wy[b]);
+            for (int b = 0; b < 7; ++b) {
+              const int y1 = yl[b + 1];
+              const float4 h0 = lerp4(__ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y0[b] * W + x0) * kD)),
+                                      __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y0[b] * W + x1) * kD)), wx);
+              const float4 h1 = lerp4(__ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y1 * W + x0) * kD)),
+                                      __ldg(reinterpret_cast<const float4*>(fm + ((int64_t)y1 * W + x1) * kD)), wx);
+              outv[b] = lerp4(h0, h1, wy[b]);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_empty[slot]);  // this warp is done reading the patch
@@ -210,9 +223,14 @@ corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int n
         mbar_wait(a_empty, (it & 1u) ^ 1u);            // MMAs of the previous tile have consumed A
         if (t < g.T) {
           uint8_t* a_hi = smem + OFF_A;
-          uint8_t* a_lo = a_hi + A_PART;
 #pragma unroll
-          for (int b = 0; b < 7; ++b) store_split4(a_hi, a_lo, 16384, f * kP + a * 7 + b, lp, outv[b]);
+          for (int b = 0; b < 7; ++b) {
+            uint32_t h0, l0, h1, l1;
+            split2(outv[b].x, outv[b].y, h0, l0);
+            split2(outv[b].z, outv[b].w, h1, l1);
+            *reinterpret_cast<uint2*>(a_hi + aoff[b]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(a_hi + A_PART + aoff[b]) = make_uint2(l0, l1);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -297,26 +315,56 @@ corr_sample_tc_kernel(CorrTcArgs g, const __grid_constant__ CorrMaps maps, int n
         __nv_bfloat16* dst_hi = reinterpret_cast<__nv_bfloat16*>(stg + f * ROW_BYTES) + rho * kP;
         __nv_bfloat16* dst_lo = dst_hi + kVolPad;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64);
+        // 49 bf16 per plane at element offset rho*49 of the row image: one 2-byte edge element (first column
+        // if that offset is odd, else the last) + 24 aligned 4-byte pairs, in two TMEM loads of 32 columns
+        const bool odd = (rho & 1) != 0;
+        uint32_t* ph = reinterpret_cast<uint32_t*>(dst_hi + (odd ? 1 : 0));
+        uint32_t* pl = reinterpret_cast<uint32_t*>(dst_lo + (odd ? 1 : 0));
         float v[32];
-        tmem_ld32(taddr, v);
+        tmem_ld32(taddr, v);                       // columns 0..31
+        const float carry = v[31];
         if (row_ok) {
+          if (odd) {
+            const bf16pair e = split_bf16(v[0]);
+            dst_hi[0] = e.hi;
+            dst_lo[0] = e.lo;
+          }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const bf16pair p = split_bf16(v[c]);
-            dst_hi[c] = p.hi;
-            dst_lo[c] = p.lo;
+          for (int j = 0; j < 15; ++j) {
+            uint32_t hi, lo;
+            split2(odd ? v[2 * j + 1] : v[2 * j], odd ? v[2 * j + 2] : v[2 * j + 1], hi, lo);
+            ph[j] = hi;
+            pl[j] = lo;
+          }
+          if (!odd) {
+            uint32_t hi, lo;
+            split2(v[30], v[31], hi, lo);
+            ph[15] = hi;
+            pl[15] = lo;
           }
         }
-        tmem_ld32(taddr + 32, v);
+        tmem_ld32(taddr + 32, v);                  // columns 32..63 (32..48 used)
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_empty[acc]);  // accumulator drained (registers hold the rest)
         if (row_ok) {
+          if (odd) {
+            uint32_t hi, lo;
+            split2(carry, v[0], hi, lo);
+            ph[15] = hi;
+            pl[15] = lo;
+          }
 #pragma unroll
-          for (int c = 0; c < kP - 32; ++c) {
-            const bf16pair p = split_bf16(v[c]);
-            dst_hi[32 + c] = p.hi;
-            dst_lo[32 + c] = p.lo;
+          for (int k = 0; k < 8; ++k) {
+            uint32_t hi, lo;
+            split2(odd ? v[2 * k + 1] : v[2 * k], odd ? v[2 * k + 2] : v[2 * k + 1], hi, lo);
+            ph[16 + k] = hi;
+            pl[16 + k] = lo;
+          }
+          if (!odd) {
+            const bf16pair e = split_bf16(v[16]);
+            dst_hi[48] = e.hi;
+            dst_lo[48] = e.lo;
           }
         }
         // all 128 epilogue threads: image complete -> coalesced copy-out of whole volume rows
