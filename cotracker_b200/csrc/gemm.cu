@@ -110,6 +110,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
   }
 }
 
+// CL = 1: independent CTAs.  CL = 2: clusters of two CTAs work on two M-tiles of the same N-tile in lockstep and
+// share the weight tile: each CTA loads half of its rows and multicasts them into both shared memories (25 % less
+// L2->SM operand traffic, which is what bounds these 128x128-tile GEMMs); smem stages are released by both MMAs.
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
                       int N, int Kpad, GemmEpilogue epi) {
@@ -128,7 +132,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);
     }
     for (int i = 0; i < ACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -139,29 +143,41 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_mt = (M + BM - 1) / BM;
+  // work items: (group of CL consecutive M-tiles, N-tile); CTA `rank` of the cluster owns M-tile mg*CL + rank
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int num_mt = ((M + BM - 1) / BM + CL - 1) / CL;   // M-tile groups
   const int num_nt = N / BN;
   const int num_tiles = num_mt * num_nt;
   const int num_kb = Kpad / BK;
+  const int first = blockIdx.x / CL, step = gridDim.x / CL;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / num_nt, nt = tile % num_nt;
+      for (int tile = first; tile < num_tiles; tile += step) {
+        const int mt = (tile / num_nt) * CL + rank, nt = tile % num_nt;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);   // CL > 1: both CTAs have consumed this stage
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           tma_load_2d(s, &tmX, kb * BK, mt * BM, &full_bar[stage]);
           tma_load_2d(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
-          tma_load_2d(s + 2 * TILE_A, &tmW, kb * BK, nt * BN, &full_bar[stage]);
-          tma_load_2d(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
+          if (CL == 1) {
+            tma_load_2d(s + 2 * TILE_A, &tmW, kb * BK, nt * BN, &full_bar[stage]);
+            tma_load_2d(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
+          } else {
+            // my half of the weight rows, multicast to both CTAs (tmW box = 64 rows in this mode)
+            const int half_bytes = TILE_B / CL, wrow = nt * BN + rank * (BN / CL);
+            tma_load_2d_mc(s + 2 * TILE_A + rank * half_bytes, &tmW, kb * BK, wrow, &full_bar[stage], (uint16_t)((1 << CL) - 1));
+            tma_load_2d_mc(s + 2 * TILE_A + TILE_B + rank * half_bytes, &tmW, Kpad + kb * BK, wrow, &full_bar[stage],
+                           (uint16_t)((1 << CL) - 1));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -172,7 +188,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < num_tiles; tile += step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -190,7 +206,8 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             umma_bf16(d_tmem, dah, dbl, idesc, 1u);
             umma_bf16(d_tmem, dah, dbh, idesc, 1u);
           }
-          umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
+          if (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          else umma_commit_mc(&empty_bar[stage], (uint16_t)((1 << CL) - 1));   // ... in both CTAs of the cluster
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
@@ -203,8 +220,8 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int chunk0 = ((warp - 2) >> 2) * (BN / 64);  // warps 2..5: columns [0,64), warps 6..9: [64,128)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / num_nt, nt = tile % num_nt;
+    for (int tile = first; tile < num_tiles; tile += step) {
+      const int mt = (tile / num_nt) * CL + rank, nt = tile % num_nt;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const int row0 = mt * BM + quarter * 32;
@@ -224,6 +241,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
   tc_fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -308,12 +326,12 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor [rows, cols] row-major, box = 64 cols (128 B) x 128 rows, 128-byte swizzle, OOB -> 0
-bool make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+bool make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows = 128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -350,21 +368,45 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
     gemm_split3_simt_kernel<<<grid, 256, 0, stream>>>(p.x_split, p.w_split, p.M, p.N, p.Kpad, p.epi);
     return (int)cudaGetLastError();
   }
+  const int num_mt = (p.M + BM - 1) / BM;
+  // clusters of 2 share the weight tile; worth it once there are enough M-tile pairs to fill the machine
+  const int cl = (impl == 0 && num_mt >= 2 * num_sms) ? 2 : 1;
   CUtensorMap tmX, tmW;
   if (!make_tmap(&tmX, p.x_split, (uint64_t)p.M, 2ull * p.Kpad) ||
-      !make_tmap(&tmW, p.w_split, (uint64_t)p.N, 2ull * p.Kpad)) {
+      !make_tmap(&tmW, p.w_split, (uint64_t)p.N, 2ull * p.Kpad, cl == 2 ? 64 : 128)) {
     *err = "gemm: cuTensorMapEncodeTiled failed";
     return (int)cudaErrorInvalidValue;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed"; return (int)e; }
     attr_set = true;
   }
-  const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  gemm_split3_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.epi);
+  if (cl == 1) {
+    const int num_tiles = num_mt * (p.N / BN);
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    gemm_split3_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.epi);
+  } else {
+    const int groups = ((num_mt + 1) / 2) * (p.N / BN);
+    int clusters = num_sms / 2;
+    if (clusters > groups) clusters = groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split3_tc_kernel<2>, tmX, tmW, p.M, p.N, p.Kpad, p.epi);
+    if (e != cudaSuccess) return (int)e;
+  }
   return (int)cudaGetLastError();
 }
 

@@ -25,7 +25,8 @@ def _rel_err(got, want):
 
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("M,K,N", [(128, 64, 128), (300, 384, 384), (1000, 2401, 384), (257, 1110, 384),
-                                   (640, 1536, 384), (4100, 384, 1536), (129, 384, 256), (64, 384, 1152)])
+                                   (640, 1536, 384), (4100, 384, 1536), (129, 384, 256), (64, 384, 1152),
+                                   (38000, 384, 384), (40100, 1110, 256)])   # >= 296 M-tiles: 2-CTA cluster path (odd tile count)
 def test_linear_matches_fp64(eng, impl, M, K, N):
     g = torch.Generator().manual_seed(M * 7 + K)
     x = torch.randn(M, K, generator=g)
@@ -222,3 +223,34 @@ def test_update_loop_vs_oracle(eng, impl):
     e_q = float((conf.cpu() - wq).abs().max())
     print("loop parity", impl, e_c, e_v, e_q)
     assert e_c < 1e-3 and e_v < 1e-3 and e_q < 1e-3
+
+
+def test_update_loop_cluster_gemm_vs_simt_at_scale(eng):
+    """N=2400, T=16: every big GEMM takes the 2-CTA multicast path; the SIMT fp32 GEMM is the on-GPU yardstick."""
+    sd = _amplified_sd(seed=9, head_gain=10.0, vis_gain=100.0)
+    T, N, H4, W4, iters = 16, 2400, 48, 64, 2
+    fmaps = _pyramid_case(T, H4, W4, seed=6)
+    pyr = eng.prepare_pyramid(fmaps.to(DEV))
+    g = torch.Generator().manual_seed(41)
+    qf = torch.randint(0, T, (N,), generator=g).to(torch.int32).to(DEV)
+    qc = (torch.rand(N, 2, generator=g) * torch.tensor([W4 - 1.0, H4 - 1.0])).to(DEV)
+    support = eng.sample_support(pyr, T, H4, W4, qf, qc)
+    packed = eng.pack_weights(sd, DEV)
+    te = O.time_embedding(sd, T)[0].contiguous().to(DEV)
+    ws = torch.empty(eng.workspace_bytes(T, N), dtype=torch.uint8, device=DEV)
+    out = {}
+    for impl in (0, 1):
+        coords = qc[None].expand(T, N, 2).contiguous().clone()
+        vis, conf = torch.zeros(T, N, device=DEV), torch.zeros(T, N, device=DEV)
+        eng.set_option("gemm", impl)
+        try:
+            eng.update_loop(packed, pyr, H4, W4, support, None, coords, vis, conf, te, iters, ws)
+            torch.cuda.synchronize()
+        finally:
+            eng.set_option("gemm", 0)
+        out[impl] = (coords.cpu(), vis.cpu(), conf.cpu())
+    assert float((out[1][0] - qc.cpu()[None]).abs().max()) > 0.25, "case must move"
+    e_c = float((out[0][0] - out[1][0]).abs().max()) * 4
+    e_v = float((out[0][1] - out[1][1]).abs().max())
+    print("cluster-vs-simt", e_c, e_v)
+    assert e_c < 5e-4 and e_v < 5e-4
