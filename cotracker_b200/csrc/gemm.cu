@@ -110,10 +110,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
   }
 }
 
-// CL = 1: independent CTAs.  CL = 2: clusters of two CTAs work on two M-tiles of the same N-tile in lockstep and
-// share the weight tile: each CTA loads half of its rows and multicasts them into both shared memories (25 % less
-// L2->SM operand traffic, which is what bounds these 128x128-tile GEMMs); smem stages are released by both MMAs.
-template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
                       int N, int Kpad, GemmEpilogue epi) {
@@ -132,7 +128,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < ACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -143,41 +139,29 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work items: (group of CL consecutive M-tiles, N-tile); CTA `rank` of the cluster owns M-tile mg*CL + rank
-  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int num_mt = ((M + BM - 1) / BM + CL - 1) / CL;   // M-tile groups
+  const int num_mt = (M + BM - 1) / BM;
   const int num_nt = N / BN;
   const int num_tiles = num_mt * num_nt;
   const int num_kb = Kpad / BK;
-  const int first = blockIdx.x / CL, step = gridDim.x / CL;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = first; tile < num_tiles; tile += step) {
-        const int mt = (tile / num_nt) * CL + rank, nt = tile % num_nt;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / num_nt, nt = tile % num_nt;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);   // CL > 1: both CTAs have consumed this stage
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           tma_load_2d(s, &tmX, kb * BK, mt * BM, &full_bar[stage]);
           tma_load_2d(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
-          if (CL == 1) {
-            tma_load_2d(s + 2 * TILE_A, &tmW, kb * BK, nt * BN, &full_bar[stage]);
-            tma_load_2d(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
-          } else {
-            // my half of the weight rows, multicast to both CTAs (tmW box = 64 rows in this mode)
-            const int half_bytes = TILE_B / CL, wrow = nt * BN + rank * (BN / CL);
-            tma_load_2d_mc(s + 2 * TILE_A + rank * half_bytes, &tmW, kb * BK, wrow, &full_bar[stage], (uint16_t)((1 << CL) - 1));
-            tma_load_2d_mc(s + 2 * TILE_A + TILE_B + rank * half_bytes, &tmW, Kpad + kb * BK, wrow, &full_bar[stage],
-                           (uint16_t)((1 << CL) - 1));
-          }
+          tma_load_2d(s + 2 * TILE_A, &tmW, kb * BK, nt * BN, &full_bar[stage]);
+          tma_load_2d(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -188,7 +172,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = first; tile < num_tiles; tile += step) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -206,8 +190,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             umma_bf16(d_tmem, dah, dbl, idesc, 1u);
             umma_bf16(d_tmem, dah, dbh, idesc, 1u);
           }
-          if (CL == 1) umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          else umma_commit_mc(&empty_bar[stage], (uint16_t)((1 << CL) - 1));   // ... in both CTAs of the cluster
+          umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);                  // accumulator complete -> epilogue
@@ -220,8 +203,8 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int chunk0 = ((warp - 2) >> 2) * (BN / 64);  // warps 2..5: columns [0,64), warps 6..9: [64,128)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first; tile < num_tiles; tile += step) {
-      const int mt = (tile / num_nt) * CL + rank, nt = tile % num_nt;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / num_nt, nt = tile % num_nt;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const int row0 = mt * BM + quarter * 32;
@@ -241,8 +224,143 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
   tc_fence_before_sync();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2).  With 128x128 tiles the tensor pipe stalls at ~55 %: every SM must
+// ingest 64 KiB of operands per 768 MMA cycles (83 B/cycle) while the L2->SM path delivers ~45 B/cycle (measured:
+// 12.7 TB/s chip-wide, profiles/).  A pair of SMs works on a 256 x BN tile instead: each CTA loads only ITS 128 rows
+// of X and ITS half (BN/2 rows) of W, one leader thread issues M=256 MMAs that read both shared memories and write
+// both TMEMs, so the bytes ingested per FLOP halve.  Both CTAs run the same producer / epilogue code on their own
+// 128 rows; barriers: full (leader, tx from both CTAs), empty + tmem_full (multicast commit to both),
+// tmem_empty (leader, remote arrives from the peer's epilogue warps).
+template <int BNP>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
+                        int N, int Kpad, GemmEpilogue epi) {
+  constexpr int TILE_BH = (BNP / 2) * BK * 2;                 // this CTA's half of the W tile, one plane
+  constexpr uint32_t TX_BYTES = 2u * (2u * TILE_A + 2u * TILE_BH);   // both CTAs, hi+lo of both operands
+  constexpr uint32_t TCOLS = 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TCOLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                            // both CTAs: barriers initialised, TMEM allocated
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_mp = ((M + BM - 1) / BM + 1) / 2;   // pairs of M-tiles
+  const int num_nt = N / BNP;
+  const int num_tiles = num_mp * num_nt;
+  const int num_kb = Kpad / BK;
+  const int first = blockIdx.x >> 1, step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first; tile < num_tiles; tile += step) {
+        const int mt = (tile / num_nt) * 2 + (int)rank, nt = tile % num_nt;
+        const int wrow = nt * BNP + (int)rank * (BNP / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], TX_BYTES);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          tma_load_2d_2sm(s, &tmX, kb * BK, mt * BM, &full_bar[stage]);
+          tma_load_2d_2sm(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
+          tma_load_2d_2sm(s + 2 * TILE_A, &tmW, kb * BK, wrow, &full_bar[stage]);
+          tma_load_2d_2sm(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, wrow, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BNP);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = first; tile < num_tiles; tile += step) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);   // both epilogues have drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BNP);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);          // both CTAs' TMA bytes have landed
+          tc_fence_after_sync();
+          const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + 2 * TILE_A, b_lo = s + 2 * TILE_A + TILE_B;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint32_t koff = kk * 32;
+            const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
+            const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
+            umma_bf16_2sm(d_tmem, dal, dbh, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, dah, dbl, idesc, 1u);
+            umma_bf16_2sm(d_tmem, dah, dbh, idesc, 1u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);          // frees the stage in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);              // accumulator complete -> both epilogues
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int quarter = warp & 3;
+    constexpr int CH = BNP / 64;                       // 32-column chunks per warp
+    const int chunk0 = ((warp - 2) >> 2) * CH;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first; tile < num_tiles; tile += step) {
+      const int mt = (tile / num_nt) * 2 + (int)rank, nt = tile % num_nt;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const int row0 = mt * BM + quarter * 32;
+      uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
+#pragma unroll 1
+      for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
+        float v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNP + chunk * 32);
+        tmem_ld32(taddr, v);
+        epilogue_chunk(epi, M, N, row0, nt * BNP + chunk * 32, lane, v, stg);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // leader's barrier (local for the leader itself)
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();                            // the pair retires together
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TCOLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -369,31 +487,33 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
     return (int)cudaGetLastError();
   }
   const int num_mt = (p.M + BM - 1) / BM;
-  // clusters of 2 share the weight tile; worth it once there are enough M-tile pairs to fill the machine
-  const int cl = (impl == 0 && num_mt >= 2 * num_sms) ? 2 : 1;
+  // CTA pairs (cta_group::2) once there is enough work to fill the machine with 256-row tiles
+  int bnp = 0;
+  if (impl == 0 && num_mt >= 2 * num_sms) bnp = (p.N % 256 == 0) ? 256 : ((p.N % 192 == 0) ? 192 : 0);
   CUtensorMap tmX, tmW;
   if (!make_tmap(&tmX, p.x_split, (uint64_t)p.M, 2ull * p.Kpad) ||
-      !make_tmap(&tmW, p.w_split, (uint64_t)p.N, 2ull * p.Kpad, cl == 2 ? 64 : 128)) {
+      !make_tmap(&tmW, p.w_split, (uint64_t)p.N, 2ull * p.Kpad, bnp ? (uint32_t)(bnp / 2) : 128u)) {
     *err = "gemm: cuTensorMapEncodeTiled failed";
     return (int)cudaErrorInvalidValue;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_pair_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed"; return (int)e; }
     attr_set = true;
   }
-  if (cl == 1) {
+  if (bnp == 0) {
     const int num_tiles = num_mt * (p.N / BN);
     const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-    gemm_split3_tc_kernel<1><<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.epi);
+    gemm_split3_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.epi);
   } else {
-    const int groups = ((num_mt + 1) / 2) * (p.N / BN);
-    int clusters = num_sms / 2;
-    if (clusters > groups) clusters = groups;
+    const int groups = ((num_mt + 1) / 2) * (p.N / bnp);
+    int pairs = num_sms / 2;
+    if (pairs > groups) pairs = groups;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
+    cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
@@ -404,7 +524,9 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_split3_tc_kernel<2>, tmX, tmW, p.M, p.N, p.Kpad, p.epi);
+    cudaError_t e = (bnp == 256)
+        ? cudaLaunchKernelEx(&cfg, gemm_split3_pair_kernel<256>, tmX, tmW, p.M, p.N, p.Kpad, p.epi)
+        : cudaLaunchKernelEx(&cfg, gemm_split3_pair_kernel<192>, tmX, tmW, p.M, p.N, p.Kpad, p.epi);
     if (e != cudaSuccess) return (int)e;
   }
   return (int)cudaGetLastError();
