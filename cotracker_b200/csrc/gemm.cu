@@ -63,26 +63,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
   }
+  // phase 2 mapping: lane -> (row rsub + 4k, 16-byte column group q): one warp instruction moves 4 rows x 128 B;
+  // reading 4 consecutive words at [row*33 + 4q] is conflict-free for this mapping ((row + 4q + i) mod 32 distinct).
+  const int rsub = lane >> 3, q = lane & 7;
   if (e.out_f32) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __float_as_uint(v[c]);
     __syncwarp();
-    float* base = e.out_f32 + (int64_t)row0 * e.ld_f32 + col0 + lane;
-    const int nrow = min(32, M - row0);   // warp-uniform
-    float x[32];
+    float* base = e.out_f32 + (int64_t)(row0 + rsub) * e.ld_f32 + col0 + 4 * q;
+    const int64_t rstep = 4 * e.ld_f32;
+    float4 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t* sp = stg + (4 * k + rsub) * 33 + 4 * q;
+      x[k] = make_float4(__uint_as_float(sp[0]), __uint_as_float(sp[1]), __uint_as_float(sp[2]), __uint_as_float(sp[3]));
+    }
     if (e.residual) {
-      // all residual rows in flight at once (v[] is dead: its registers are reused)
+      float4 r[8];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) x[r] = r < nrow ? base[(int64_t)r * e.ld_f32] : 0.f;
+      for (int k = 0; k < 8; ++k)   // all residual rows in flight at once
+        r[k] = (row0 + 4 * k + rsub < M) ? *reinterpret_cast<const float4*>(base + k * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < 32; ++r) x[r] += __uint_as_float(stg[r * 33 + lane]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < 32; ++r) x[r] = __uint_as_float(stg[r * 33 + lane]);
+      for (int k = 0; k < 8; ++k) { x[k].x += r[k].x; x[k].y += r[k].y; x[k].z += r[k].z; x[k].w += r[k].w; }
     }
 #pragma unroll
-    for (int r = 0; r < 32; ++r)
-      if (r < nrow) base[(int64_t)r * e.ld_f32] = x[r];
+    for (int k = 0; k < 8; ++k)
+      if (row0 + 4 * k + rsub < M) *reinterpret_cast<float4*>(base + k * rstep) = x[k];
     __syncwarp();
   }
   if (e.out_split) {
@@ -90,21 +96,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
     for (int i = 0; i < 16; ++i) {
       uint32_t hi, lo;
       split2(v[2 * i], v[2 * i + 1], hi, lo);
-      stg[lane * 33 + i] = hi;
-      stg[lane * 33 + 16 + i] = lo;
+      stg[lane * 33 + i] = hi;          // words 0..15 : hi plane of this row (32 bf16)
+      stg[lane * 33 + 16 + i] = lo;     // words 16..31: lo plane
     }
     __syncwarp();
-    // element offset of this lane's row (one division per chunk); broadcast per row with a shuffle below
-    long long off_lane = -1;
+    // output offset of this lane's row in 16-byte units (every offset is a multiple of 32 elements); one division
+    // per chunk, then one 32-bit shuffle per stored row group
+    uint32_t off16_lane = 0xffffffffu;
     if (row < M) {
       const int orow = row / e.row_group;
-      off_lane = (long long)orow * e.ld_split + (long long)(row % e.row_group) * N + col0;
+      off16_lane = (uint32_t)(((long long)orow * e.ld_split + (long long)(row % e.row_group) * N + col0) >> 3);
     }
-    const int half = lane >> 4, w = lane & 15;   // lanes 0..15: hi plane, 16..31: lo plane
+    uint4* plane = reinterpret_cast<uint4*>(e.out_split + (q >= 4 ? e.lo_off : 0)) + (q & 3);
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const long long off = __shfl_sync(0xffffffffu, off_lane, r);
-      if (off >= 0) reinterpret_cast<uint32_t*>(e.out_split + off + half * e.lo_off)[w] = stg[r * 33 + lane];
+    for (int k = 0; k < 8; ++k) {
+      const int r = 4 * k + rsub;
+      const uint32_t o16 = __shfl_sync(0xffffffffu, off16_lane, r);
+      const uint32_t* sp = stg + r * 33 + 4 * q;
+      const uint4 w4 = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+      if (o16 != 0xffffffffu) plane[o16] = w4;
     }
     __syncwarp();
   }
