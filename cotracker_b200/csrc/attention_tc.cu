@@ -31,7 +31,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 
 template <int KB, bool PER_WARP>
 __global__ void __launch_bounds__(WARPS * 32)
-attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, float* part_o) {
+attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, int qtw, float* part_ml, float* part_o) {
   constexpr int VPAD = KB + 8;  // bf16 row stride of V^T tiles
   constexpr int SLICE = 2 * KB * KPAD + 2 * kDh * VPAD;  // bf16 elements per K/V staging slice
   extern __shared__ __align__(16) uint8_t att_smem[];
@@ -53,17 +53,28 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
     s = blockIdx.x;
     h = blockIdx.y % kHeads;
     const int qb = blockIdx.y / kHeads;
-    qt = qb * WARPS + warp;
+    qt = (qb * WARPS + warp) * qtw;   // first of the qtw query tiles this warp walks (single-chunk K/V only)
     split = blockIdx.z;
-    active = qt < q_tiles;
-    if (!active) qt = q_tiles - 1;
   }
+  const int qt_first = qt;
+  const bool item_ok = active;
   __nv_bfloat16* slice = reinterpret_cast<__nv_bfloat16*>(att_smem) + (PER_WARP ? warp * SLICE : 0);
   __nv_bfloat16* Kh = slice;
   __nv_bfloat16* Kl = Kh + KB * KPAD;
   __nv_bfloat16* Vh = Kl + KB * KPAD;   // V^T [48][VPAD]
   __nv_bfloat16* Vl = Vh + kDh * VPAD;
 
+  // key range of this CTA (split-K) in units of chunks
+  const int chunks = (p.Lk + KB - 1) / KB;
+  const int c_per = (chunks + num_splits - 1) / num_splits;
+  const int c_begin = split * c_per, c_end = min(chunks, c_begin + c_per);
+
+  // K/V are staged once when they fit one chunk; the warp then walks qtw query tiles against them
+  for (int ti = 0; ti < qtw; ++ti) {
+  qt = qt_first + ti;
+  active = item_ok && qt < q_tiles;
+  if (qt >= q_tiles) qt = q_tiles - 1;
+  const bool stage_now = (ti == 0) || (c_end - c_begin > 1);
   // ---- Q fragments (rows g and g+8 of the tile), split hi/lo
   const int q_row0 = qt * 16 + g, q_row1 = q_row0 + 8;
   uint32_t qh[3][4], ql[3][4];
@@ -89,15 +100,10 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
   for (int nd = 0; nd < 6; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  // key range of this CTA (split-K) in units of chunks
-  const int chunks = (p.Lk + KB - 1) / KB;
-  const int c_per = (chunks + num_splits - 1) / num_splits;
-  const int c_begin = split * c_per, c_end = min(chunks, c_begin + c_per);
-
   for (int c = c_begin; c < c_end; ++c) {
     const int kc0 = c * KB;
     // ---- stage K (row-major) and V^T, split hi/lo; zero-fill past Lk
-    {
+    if (stage_now) {
       const int nthr = PER_WARP ? 32 : WARPS * 32;
       const int tid = PER_WARP ? lane : threadIdx.x;
       for (int idx = tid; idx < KB * (kDh / 4); idx += nthr) {
@@ -122,7 +128,7 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
         }
       }
     }
-    if (PER_WARP) __syncwarp(); else __syncthreads();
+    if (stage_now) { if (PER_WARP) __syncwarp(); else __syncthreads(); }
 
     // ---- S = Q K^T  (16 x KB per warp)
     float sc[KB / 8][4];
@@ -188,7 +194,7 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
         mma16816(o[nd], ph, bh0, bh1);
       }
     }
-    if (PER_WARP) __syncwarp(); else __syncthreads();
+    if (c_end - c_begin > 1) { if (PER_WARP) __syncwarp(); else __syncthreads(); }   // smem is restaged next chunk
   }
 
   // ---- finish: row sums across the quad, normalise, store
@@ -196,7 +202,7 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  if (!active) return;
+  if (!active) continue;
   if (num_splits > 1) {
     // partials: item = ((s*heads + h)*num_splits + split); rows indexed by query
     const int64_t item = ((int64_t)s * kHeads + h) * num_splits + split;
@@ -212,7 +218,7 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
 #pragma unroll
       for (int nd = 0; nd < 6; ++nd) *reinterpret_cast<float2*>(po + (int64_t)q_row1 * kDh + nd * 8 + 2 * t4) = make_float2(o[nd][2], o[nd][3]);
     }
-    return;
+    continue;
   }
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
   if (q_row0 < p.Lq) {
@@ -235,6 +241,7 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, float* part_ml, f
       *reinterpret_cast<uint32_t*>(orow + p.lo_off + nd * 8 + 2 * t4) = lo;
     }
   }
+  }  // ti
 }
 
 // merge split-K partials: one warp per (s, h, query); lanes over the 48 output channels
@@ -275,7 +282,7 @@ attention_combine_kernel(AttnParams p, int num_splits, const float* __restrict__
 }
 
 template <int KB, bool PER_WARP>
-cudaError_t launch_variant(const AttnParams& p, int num_splits, float* part_ml, float* part_o, cudaStream_t s) {
+cudaError_t launch_variant(const AttnParams& p, int num_splits, int qtw, float* part_ml, float* part_o, cudaStream_t s) {
   constexpr int VPAD = KB + 8;
   constexpr int SLICE_BYTES = (2 * KB * KPAD + 2 * kDh * VPAD) * 2;
   const int smem = SLICE_BYTES * (PER_WARP ? WARPS : 1);
@@ -290,12 +297,12 @@ cudaError_t launch_variant(const AttnParams& p, int num_splits, float* part_ml, 
     const long long items = (long long)p.num_seq * kHeads * q_tiles;
     const long long blocks = (items + WARPS - 1) / WARPS;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    attention_tc_kernel<KB, true><<<(unsigned)blocks, WARPS * 32, smem, s>>>(p, q_tiles, 1, nullptr, nullptr);
+    attention_tc_kernel<KB, true><<<(unsigned)blocks, WARPS * 32, smem, s>>>(p, q_tiles, 1, 1, nullptr, nullptr);
   } else {
-    const int qblocks = (q_tiles + WARPS - 1) / WARPS;
+    const int qblocks = (q_tiles + WARPS * qtw - 1) / (WARPS * qtw);
     dim3 grid(p.num_seq, kHeads * qblocks, num_splits);
     if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
-    attention_tc_kernel<KB, false><<<grid, WARPS * 32, smem, s>>>(p, q_tiles, num_splits, part_ml, part_o);
+    attention_tc_kernel<KB, false><<<grid, WARPS * 32, smem, s>>>(p, q_tiles, num_splits, qtw, part_ml, part_o);
   }
   return cudaGetLastError();
 }
@@ -311,9 +318,9 @@ size_t attention_partial_bytes(int num_seq, int Lq, int max_splits) {
 cudaError_t launch_attention_tc(const AttnParams& p, bool per_warp, float* part, int num_sms, cudaStream_t s) {
   if (p.num_seq <= 0 || p.Lq <= 0 || p.Lk <= 0) return cudaSuccess;
   if (per_warp) {
-    if (p.Lk <= 16) return launch_variant<16, true>(p, 1, nullptr, nullptr, s);
-    if (p.Lk <= 32) return launch_variant<32, true>(p, 1, nullptr, nullptr, s);
-    return launch_variant<64, true>(p, 1, nullptr, nullptr, s);
+    if (p.Lk <= 16) return launch_variant<16, true>(p, 1, 1, nullptr, nullptr, s);
+    if (p.Lk <= 32) return launch_variant<32, true>(p, 1, 1, nullptr, nullptr, s);
+    return launch_variant<64, true>(p, 1, 1, nullptr, nullptr, s);
   }
   // split-K when the query side alone cannot fill the machine
   const int q_tiles = (p.Lq + 15) / 16;
@@ -326,10 +333,16 @@ cudaError_t launch_attention_tc(const AttnParams& p, bool per_warp, float* part,
     if (splits > chunks / 2) splits = chunks / 2;
     if (splits < 1) splits = 1;
   }
-  if (splits == 1) return launch_variant<64, false>(p, 1, nullptr, nullptr, s);
+  if (splits == 1) {
+    // K/V of one chunk are staged once per CTA: amortise the conversion over several query tiles per warp while
+    // still leaving >= 4 CTAs per SM
+    int qtw = 1;
+    if (chunks == 1) while (qtw < 8 && (long long)p.num_seq * kHeads * ((q_tiles + WARPS * 2 * qtw - 1) / (WARPS * 2 * qtw)) >= 4LL * num_sms) qtw *= 2;
+    return launch_variant<64, false>(p, 1, qtw, nullptr, nullptr, s);
+  }
   float* part_ml = part;
   float* part_o = part + (size_t)p.num_seq * kHeads * splits * p.Lq * 2;
-  cudaError_t e = launch_variant<64, false>(p, splits, part_ml, part_o, s);
+  cudaError_t e = launch_variant<64, false>(p, splits, 1, part_ml, part_o, s);
   if (e != cudaSuccess) return e;
   const int64_t rows = (int64_t)p.num_seq * kHeads * p.Lq;
   attention_combine_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(p, splits, part_ml, part_o);
