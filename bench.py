@@ -254,6 +254,11 @@ def main():
     cat_ms, cat_n, gemm_flops = engine.profile_read()
     engine.profile_enable(False)
     pk = peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")   # ncu-measured DRAM bytes of one headline step
+    if os.path.exists(tp) and T == T_FRAMES and G == GRID:
+        with open(tp) as f:
+            traffic = json.load(f)
     gemm_tflops = gemm_flops / (cat_ms["gemm"] / 1e3) / 1e12 if cat_ms["gemm"] > 0 else 0.0
     # pyramid read once (16320 texels/frame at the 384x512 model resolution) + support + coords + volume write
     corr_bytes = ITERS * (T * 16320 * 128 * 4 + N * 4 * 49 * 128 * 4 + T * N * 8 + T * N * 4 * 2401 * 4)
@@ -274,12 +279,17 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "gemm_split3_tc_kernel (tcgen05, all linear layers)", "bound": "tensor",
                      "achieved": gemm_tflops, "peak": pk["bf16"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / pk["bf16"], "traffic": None,
+                     "frac": gemm_tflops / pk["bf16"],
+                     "traffic": traffic.get("gemm", {}).get("dram_bytes_per_step"),
+                     "traffic_note": "ncu dram__bytes_read+write summed over the step's GEMM launches (profiles/"
+                                     "r1_dram_traffic.json); algorithmic operand+result bytes are 24.0 GB/iteration x 6",
                      "note": "algorithmic fp32-equivalent FLOPs; each is 3 bf16 tensor-core products, so the "
                              "tensor pipe is busy at 3x this fraction; peak = sustained cuBLAS bf16 (" + pk["source"] + ")",
                      "ms_per_step": cat_ms["gemm"], "launches_per_step": cat_n["gemm"]},
         "roofline_corr": {"kernel": "corr_sample", "bound": "hbm", "achieved": corr_gbs, "peak": pk["hbm"],
-                          "unit": "GB/s", "frac": corr_gbs / pk["hbm"], "traffic": None,
+                          "unit": "GB/s", "frac": corr_gbs / pk["hbm"],
+                          "traffic": traffic.get("corr_sample", {}).get("dram_bytes_per_step"),
+                          "algorithmic_bytes_per_step": corr_bytes,
                           "ms_per_step": cat_ms["corr_sample"], "launches_per_step": cat_n["corr_sample"]},
         "kernel_ms_per_step": cat_ms, "library_ms_per_step": lib_ms,
     }
