@@ -3,7 +3,7 @@
 // Persistent warp-specialised kernel, one CTA per SM:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 3-stage ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (3 MMAs per k16 step: hi*hi, lo*hi, hi*lo)
-//   warps 2..9  : epilogue       (tcgen05.ld -> bias / row-bias / GELU / residual -> fp32 and/or split-bf16 stores)
+//   warps 2..17 : epilogue       (tcgen05.ld -> bias / row-bias / GELU / residual -> fp32 and/or split-bf16 stores)
 // Two 128-column fp32 accumulators in TMEM are double buffered so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Tiles are 128 x 128; consecutive tile ids share the X (activation) tile so the
 // big operand is read from HBM once and hit in L2 by the CTAs working on its other N-tiles.
@@ -20,8 +20,9 @@ constexpr int STAGES = 3, ACC = 2;
 constexpr int TILE_A = BM * BK * 2;                    // 16 KiB (bf16)
 constexpr int TILE_B = BN * BK * 2;                    // 16 KiB
 constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;   // hi+lo of both operands = 64 KiB
-constexpr int EPI_WARPS = 8;                           // two warps per TMEM lane quarter, half the columns each
-constexpr int STG_WORDS = 32 * 33;                     // per-warp transpose buffer (padded: conflict-free both ways)
+constexpr int EPI_WARPS = 16;                          // four warps per TMEM lane quarter, a quarter of the columns each
+constexpr int CW = 16;                                 // epilogue chunk width (columns)
+constexpr int STG_WORDS = 32 * CW;                     // per-warp transpose buffer (rotated rows: conflict-free both ways)
 constexpr int OFF_STG = STAGES * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_WORDS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 128 /*barriers*/ + 1024 /*align slack*/;
@@ -35,18 +36,20 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// Epilogue of one 32-row x 32-column chunk by one warp.  Phase 1 (lane = row, straight out of tcgen05.ld):
-// bias / row-bias / activation, then the 32 output words of the row (fp32, or 16 packed-hi | 16 packed-lo bf16
-// pairs) go to a padded (stride 33) per-warp staging buffer.  Phase 2 (lane = word): every global access of the
-// warp is one contiguous 128-byte (fp32) or 2 x 64-byte (split planes) row segment -- 8x fewer LSU wavefronts
-// than letting each thread stream its own row.
+// Epilogue of one 32-row x 16-column chunk by one warp.  Phase 1 (lane = row, straight out of tcgen05.ld): bias /
+// row-bias / activation, then the 16 output words of the row (16 fp32, or 8 packed-hi | 8 packed-lo bf16 pairs) go to
+// a per-warp staging buffer whose rows are rotated by row/2 words (conflict-free for both access patterns without
+// padding).  Phase 2 (lane = (row in a group of 8, 16-byte column group)): every warp instruction moves 8 rows x 64 B
+// of global memory in whole 32-byte sectors.
+__device__ __forceinline__ int stg_idx(int row, int word) { return row * CW + ((word + (row >> 1)) & (CW - 1)); }
+
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int N, int row0, int col0, int lane,
-                                               float (&v)[32], uint32_t* stg) {
+                                               float (&v)[CW], uint32_t* stg) {
   const int row = row0 + lane;
   if (e.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CW / 4; ++i) {
       float4 b = __ldg(b4 + i);
       v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
@@ -54,66 +57,65 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
   if (e.row_bias && row < M) {
     const float4* b4 = reinterpret_cast<const float4*>(e.row_bias + (int64_t)(row % e.row_mod) * N + col0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CW / 4; ++i) {
       float4 b = __ldg(b4 + i);
       v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
   }
   if (e.act != 0) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], e.act);
+    for (int i = 0; i < CW; ++i) v[i] = apply_act(v[i], e.act);
   }
-  // phase 2 mapping: lane -> (row rsub + 4k, 16-byte column group q): one warp instruction moves 4 rows x 128 B;
-  // reading 4 consecutive words at [row*33 + 4q] is conflict-free for this mapping ((row + 4q + i) mod 32 distinct).
-  const int rsub = lane >> 3, q = lane & 7;
+  const int rsub = lane >> 2, q = lane & 3;   // phase-2 mapping: rows rsub + 8k, 16-byte group q of the 64-byte row
   if (e.out_f32) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __float_as_uint(v[c]);
+    for (int c = 0; c < CW; ++c) stg[stg_idx(lane, c)] = __float_as_uint(v[c]);
     __syncwarp();
     float* base = e.out_f32 + (int64_t)(row0 + rsub) * e.ld_f32 + col0 + 4 * q;
-    const int64_t rstep = 4 * e.ld_f32;
-    float4 x[8];
+    const int64_t rstep = 8 * e.ld_f32;
+    float4 x[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t* sp = stg + (4 * k + rsub) * 33 + 4 * q;
-      x[k] = make_float4(__uint_as_float(sp[0]), __uint_as_float(sp[1]), __uint_as_float(sp[2]), __uint_as_float(sp[3]));
+    for (int k = 0; k < 4; ++k) {
+      const int r = 8 * k + rsub;
+      x[k] = make_float4(__uint_as_float(stg[stg_idx(r, 4 * q + 0)]), __uint_as_float(stg[stg_idx(r, 4 * q + 1)]),
+                         __uint_as_float(stg[stg_idx(r, 4 * q + 2)]), __uint_as_float(stg[stg_idx(r, 4 * q + 3)]));
     }
     if (e.residual) {
-      float4 r[8];
+      float4 r4[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)   // all residual rows in flight at once
-        r[k] = (row0 + 4 * k + rsub < M) ? *reinterpret_cast<const float4*>(base + k * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 4; ++k)   // all residual rows in flight at once
+        r4[k] = (row0 + 8 * k + rsub < M) ? *reinterpret_cast<const float4*>(base + k * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { x[k].x += r[k].x; x[k].y += r[k].y; x[k].z += r[k].z; x[k].w += r[k].w; }
+      for (int k = 0; k < 4; ++k) { x[k].x += r4[k].x; x[k].y += r4[k].y; x[k].z += r4[k].z; x[k].w += r4[k].w; }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (row0 + 4 * k + rsub < M) *reinterpret_cast<float4*>(base + k * rstep) = x[k];
+    for (int k = 0; k < 4; ++k)
+      if (row0 + 8 * k + rsub < M) *reinterpret_cast<float4*>(base + k * rstep) = x[k];
     __syncwarp();
   }
   if (e.out_split) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < CW / 2; ++i) {
       uint32_t hi, lo;
       split2(v[2 * i], v[2 * i + 1], hi, lo);
-      stg[lane * 33 + i] = hi;          // words 0..15 : hi plane of this row (32 bf16)
-      stg[lane * 33 + 16 + i] = lo;     // words 16..31: lo plane
+      stg[stg_idx(lane, i)] = hi;              // words 0..7 : hi plane of this row (16 bf16)
+      stg[stg_idx(lane, CW / 2 + i)] = lo;     // words 8..15: lo plane
     }
     __syncwarp();
-    // output offset of this lane's row in 16-byte units (every offset is a multiple of 32 elements); one division
+    // output offset of this lane's row in 16-byte units (every offset is a multiple of 16 elements); one division
     // per chunk, then one 32-bit shuffle per stored row group
     uint32_t off16_lane = 0xffffffffu;
     if (row < M) {
       const int orow = row / e.row_group;
       off16_lane = (uint32_t)(((long long)orow * e.ld_split + (long long)(row % e.row_group) * N + col0) >> 3);
     }
-    uint4* plane = reinterpret_cast<uint4*>(e.out_split + (q >= 4 ? e.lo_off : 0)) + (q & 3);
+    uint4* plane = reinterpret_cast<uint4*>(e.out_split + (q >= 2 ? e.lo_off : 0)) + (q & 1);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = 4 * k + rsub;
+    for (int k = 0; k < 4; ++k) {
+      const int r = 8 * k + rsub;
       const uint32_t o16 = __shfl_sync(0xffffffffu, off16_lane, r);
-      const uint32_t* sp = stg + r * 33 + 4 * q;
-      const uint4 w4 = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+      const uint4 w4 = make_uint4(stg[stg_idx(r, 4 * q + 0)], stg[stg_idx(r, 4 * q + 1)], stg[stg_idx(r, 4 * q + 2)],
+                                  stg[stg_idx(r, 4 * q + 3)]);
       if (o16 != 0xffffffffu) plane[o16] = w4;
     }
     __syncwarp();
@@ -210,7 +212,8 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warp id % 4)
-    const int chunk0 = ((warp - 2) >> 2) * (BN / 64);  // warps 2..5: columns [0,64), warps 6..9: [64,128)
+    constexpr int CH = BN / CW / (EPI_WARPS / 4);      // 16-column chunks per warp
+    const int chunk0 = ((warp - 2) >> 2) * CH;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -220,11 +223,11 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const int row0 = mt * BM + quarter * 32;
       uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
 #pragma unroll 1
-      for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
-        float v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * 32);
-        tmem_ld32(taddr, v);
-        epilogue_chunk(epi, M, N, row0, nt * BN + chunk * 32, lane, v, stg);
+      for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
+        float v[CW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * CW);
+        tmem_ld16(taddr, v);
+        epilogue_chunk(epi, M, N, row0, nt * BN + chunk * CW, lane, v, stg);
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty_bar[acc]);
@@ -343,7 +346,7 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
     const int quarter = warp & 3;
-    constexpr int CH = BNP / 64;                       // 32-column chunks per warp
+    constexpr int CH = BNP / CW / (EPI_WARPS / 4);     // 16-column chunks per warp
     const int chunk0 = ((warp - 2) >> 2) * CH;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -355,10 +358,10 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
 #pragma unroll 1
       for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
-        float v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNP + chunk * 32);
-        tmem_ld32(taddr, v);
-        epilogue_chunk(epi, M, N, row0, nt * BNP + chunk * 32, lane, v, stg);
+        float v[CW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNP + chunk * CW);
+        tmem_ld16(taddr, v);
+        epilogue_chunk(epi, M, N, row0, nt * BNP + chunk * CW, lane, v, stg);
       }
       tc_fence_before_sync();
       __syncwarp();
