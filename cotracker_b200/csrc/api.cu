@@ -605,3 +605,112 @@ int ct3_updateformer(const void* packed, const float* x, int T, int N, float* de
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// encoder tail (conv2 -> InstanceNorm -> ReLU -> conv3 -> L2-normalise -> pyramid), see enc_tail.cu
+namespace {
+constexpr int kEncCin = 416, kEncMid = 256, kEncK = kEncCin * 9;
+struct EncLayout { Lin conv2, conv3; size_t total; };
+const EncLayout& enc_layout() {
+  static EncLayout E;
+  static bool init = false;
+  if (!init) {
+    size_t off = 0;
+    place_lin(E.conv2, kEncMid, kEncK, off);
+    place_lin(E.conv3, kD, kEncMid, off);
+    E.total = off;
+    init = true;
+  }
+  return E;
+}
+struct EncWs { __nv_bfloat16* a; float* y; __nv_bfloat16* ys; float* stats; size_t total; int tc; };
+EncWs enc_carve(void* base, int T, int H4, int W4) {
+  EncWs w;
+  w.tc = T < 16 ? T : 16;                         // frames per chunk: bounds the im2col operand to ~3 GB
+  const size_t Mc = (size_t)w.tc * H4 * W4;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* r = p + off; off = align_up(off + bytes, 1024); return r; };
+  w.a = (__nv_bfloat16*)take(Mc * 2 * pad64(kEncK) * 2);
+  w.y = (float*)take(Mc * kEncMid * 4);
+  w.ys = (__nv_bfloat16*)take(Mc * 2 * kEncMid * 2);
+  w.stats = (float*)take((size_t)w.tc * kEncMid * 2 * 4);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+int ct3_enc_tail_packed_bytes(size_t* out_bytes) {
+  if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
+  *out_bytes = enc_layout().total;
+  return 0;
+}
+
+int ct3_enc_tail_pack(const float* conv2_w, const float* conv2_b, const float* conv3_w, const float* conv3_b,
+                      void* packed, size_t packed_bytes, ct3_stream_t stream) {
+  const EncLayout& E = enc_layout();
+  if (!conv2_w || !conv2_b || !conv3_w || !conv3_b || !packed) return fail(CT3_EINVAL, "null argument%s");
+  if (packed_bytes < E.total) return fail(CT3_ENOSPC, "packed buffer too small%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
+  CK(cudaMemsetAsync(pk, 0, E.total, s), "memset enc packed");
+  CK(launch_split_rows(conv2_w, kEncMid, kEncK, E.conv2.Kpad, 0, reinterpret_cast<__nv_bfloat16*>(pk + E.conv2.w), 0, s), "pack conv2");
+  CK(cudaMemcpyAsync(pk + E.conv2.b, conv2_b, kEncMid * 4, cudaMemcpyDeviceToDevice, s), "pack conv2 bias");
+  CK(launch_split_rows(conv3_w, kD, kEncMid, E.conv3.Kpad, 0, reinterpret_cast<__nv_bfloat16*>(pk + E.conv3.w), 0, s), "pack conv3");
+  CK(cudaMemcpyAsync(pk + E.conv3.b, conv3_b, kD * 4, cudaMemcpyDeviceToDevice, s), "pack conv3 bias");
+  return 0;
+}
+
+int ct3_enc_tail_workspace_bytes(int T, int H4, int W4, size_t* out_bytes) {
+  if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  *out_bytes = enc_carve(nullptr, T, H4, W4).total;
+  return 0;
+}
+
+int ct3_enc_tail(const void* packed, const float* cat, int T, int H4, int W4, float* pyr, void* workspace,
+                 size_t workspace_bytes, ct3_stream_t stream) {
+  if (!packed || !cat || !pyr || !workspace) return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  if ((uintptr_t)workspace & 255) return fail(CT3_EINVAL, "workspace must be 256-byte aligned%s");
+  const EncWs W = enc_carve(workspace, T, H4, W4);
+  if (workspace_bytes < W.total) return fail(CT3_ENOSPC, "workspace too small%s");
+  const EncLayout& E = enc_layout();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = H4 * W4;
+  const PyramidLayout lay = pyramid_layout(T, H4, W4);
+  for (int t0 = 0; t0 < T; t0 += W.tc) {
+    const int tc = (T - t0) < W.tc ? (T - t0) : W.tc;
+    const int Mc = tc * HW;
+    const float* in = cat + (int64_t)t0 * kEncCin * HW;
+    float* f0 = pyr + lay.off[0] + (int64_t)t0 * HW * kD;   // conv3 rows (t,y,x) are the channels-last texels
+    CK(launch_im2col3x3_split(in, tc, kEncCin, H4, W4, E.conv2.Kpad, W.a, s), "im2col conv2");
+    const char* gerr = nullptr;
+    GemmProblem p;
+    p.x_split = W.a;
+    p.w_split = reinterpret_cast<const __nv_bfloat16*>(pk + E.conv2.w);
+    p.M = Mc; p.N = kEncMid; p.Kpad = E.conv2.Kpad;
+    p.epi.bias = reinterpret_cast<const float*>(pk + E.conv2.b);
+    p.epi.out_f32 = W.y; p.epi.ld_f32 = kEncMid;
+    int rc = gemm_launch(p, g_opt_gemm, num_sms(), s, &gerr);
+    if (rc != 0) { snprintf(g_err, sizeof(g_err), "enc conv2 gemm: %s (%s)", cudaGetErrorString((cudaError_t)rc), gerr ? gerr : ""); return CT3_ECUDA; }
+    CK(launch_instnorm_stats(W.y, tc, HW, kEncMid, 1e-5f, W.stats, s), "instnorm stats");
+    CK(launch_instnorm_relu_split(W.y, W.stats, (int64_t)Mc, HW, kEncMid, W.ys, s), "instnorm relu split");
+    GemmProblem q;
+    q.x_split = W.ys;
+    q.w_split = reinterpret_cast<const __nv_bfloat16*>(pk + E.conv3.w);
+    q.M = Mc; q.N = kD; q.Kpad = E.conv3.Kpad;
+    q.epi.bias = reinterpret_cast<const float*>(pk + E.conv3.b);
+    q.epi.out_f32 = f0; q.epi.ld_f32 = kD;
+    rc = gemm_launch(q, g_opt_gemm, num_sms(), s, &gerr);
+    if (rc != 0) { snprintf(g_err, sizeof(g_err), "enc conv3 gemm: %s (%s)", cudaGetErrorString((cudaError_t)rc), gerr ? gerr : ""); return CT3_ECUDA; }
+    CK(launch_l2norm_rows(f0, (int64_t)Mc, f0, s), "l2norm rows");
+  }
+  CK(launch_pyramid_pools(T, H4, W4, pyr, s), "pyramid pools");
+  return 0;
+}
+
+}  // extern "C"

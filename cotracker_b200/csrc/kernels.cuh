@@ -16,6 +16,17 @@ cudaError_t launch_sample_support(const float* pyr, int T, int H4, int W4, const
                                   const float* qcoords, int N, const uint8_t* acc_mask, float* support,
                                   cudaStream_t s);
 
+// pools levels 1..3 from an already normalised channels-last level 0 living in `pyr`
+cudaError_t launch_pyramid_pools(int T, int H4, int W4, float* pyr, cudaStream_t s);
+
+// ---- enc_tail.cu : conv2 -> InstanceNorm -> ReLU -> conv3 of the encoder on the GEMM engine --------
+cudaError_t launch_im2col3x3_split(const float* in, int T, int C, int H, int W, int Kpad, __nv_bfloat16* out,
+                                   cudaStream_t s);
+cudaError_t launch_instnorm_stats(const float* y, int T, int HW, int C, float eps, float* stats, cudaStream_t s);
+cudaError_t launch_instnorm_relu_split(const float* y, const float* stats, int64_t rows, int HW, int C,
+                                       __nv_bfloat16* out, cudaStream_t s);
+cudaError_t launch_l2norm_rows(const float* in, int64_t rows, float* out, cudaStream_t s);
+
 // ---- corr.cu : correlation sampling ---------------------------------------------------------------
 // vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level
 cudaError_t launch_corr_sample(const float* pyr, int H4, int W4, const float* support,

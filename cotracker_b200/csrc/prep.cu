@@ -111,6 +111,18 @@ sample_support_kernel(const float* __restrict__ pyr, PyramidLayout lay, int T, c
 
 }  // namespace
 
+cudaError_t launch_pyramid_pools(int T, int H4, int W4, float* pyr, cudaStream_t s) {
+  const PyramidLayout lay = pyramid_layout(T, H4, W4);
+  for (int l = 1; l < kL; ++l) {
+    const int64_t total = (int64_t)T * lay.h[l] * lay.w[l] * (kD / 4);
+    if (total == 0) continue;
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    avgpool2_channels_last_kernel<<<blocks, 256, 0, s>>>(pyr + lay.off[l - 1], pyr + lay.off[l], T, lay.h[l - 1],
+                                                        lay.w[l - 1], lay.h[l], lay.w[l]);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prepare_pyramid(const float* fmaps, int T, int H4, int W4, float* pyr, cudaStream_t s) {
   const PyramidLayout lay = pyramid_layout(T, H4, W4);
   dim3 g((W4 + 31) / 32, H4, T);

@@ -54,7 +54,8 @@ class BasicEncoder(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
-    def forward(self, x):
+    def forward_front(self, x):
+        """Stem + four residual stages + resize + concat -> [T, 416, H/4, W/4] (the input of conv2)."""
         H, W = x.shape[-2:]
         size = (H // self.stride, W // self.stride)
         x = F.relu(F.instance_norm(self.conv1(x)))
@@ -62,5 +63,8 @@ class BasicEncoder(nn.Module):
         for i in range(1, 5):
             x = getattr(self, f"layer{i}")(x)
             feats.append(F.interpolate(x, size, mode="bilinear", align_corners=True))
-        x = F.relu(F.instance_norm(self.conv2(torch.cat(feats, dim=1))))
+        return torch.cat(feats, dim=1)
+
+    def forward(self, x):
+        x = F.relu(F.instance_norm(self.conv2(self.forward_front(x))))
         return self.conv3(x)

@@ -48,6 +48,10 @@ def _declare(lib):
         "ct3_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_split_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_updateformer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "ct3_enc_tail_packed_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
+        "ct3_enc_tail_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "ct3_enc_tail_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+        "ct3_enc_tail": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
         "ct3_profile_enable": (c_int, [c_int]),
         "ct3_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), intp, ctypes.POINTER(ctypes.c_double)]),
     }
@@ -63,6 +67,7 @@ EXPORTED_SYMBOLS = [
     "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
     "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
     "ct3_corr_sample", "ct3_linear", "ct3_split_rows", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
+    "ct3_enc_tail_packed_bytes", "ct3_enc_tail_pack", "ct3_enc_tail_workspace_bytes", "ct3_enc_tail",
 ]
 
 
@@ -288,3 +293,46 @@ def profile_read():
     fl = ctypes.c_double(0)
     _check(lib().ct3_profile_read(ms, n, ctypes.byref(fl)), "ct3_profile_read")
     return dict(zip(PROFILE_CATEGORIES, list(ms))), dict(zip(PROFILE_CATEGORIES, list(n))), fl.value
+
+
+# ---- encoder tail -------------------------------------------------------------------------------------
+def enc_tail_pack(conv2_w, conv2_b, conv3_w, conv3_b, device) -> torch.Tensor:
+    n = ctypes.c_size_t(0)
+    _check(lib().ct3_enc_tail_packed_bytes(ctypes.byref(n)), "ct3_enc_tail_packed_bytes")
+    ts = [x.detach().to(device=device, dtype=torch.float32).contiguous() for x in (conv2_w, conv2_b, conv3_w, conv3_b)]
+    packed = torch.empty(n.value, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _check(lib().ct3_enc_tail_pack(_ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(ts[3]), _ptr(packed), n.value,
+                                       _stream(device)), "ct3_enc_tail_pack")
+        torch.cuda.current_stream(device).synchronize()
+    return packed
+
+
+def enc_tail_workspace_bytes(T: int, H4: int, W4: int) -> int:
+    n = ctypes.c_size_t(0)
+    _check(lib().ct3_enc_tail_workspace_bytes(T, H4, W4, ctypes.byref(n)), "ct3_enc_tail_workspace_bytes")
+    return n.value
+
+
+def enc_tail(packed, cat: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor:
+    """cat [T,416,H4,W4] fp32 -> flat channels-last normalised pyramid (same layout as prepare_pyramid)."""
+    _req(cat, torch.float32, "cat")
+    T, C, H4, W4 = cat.shape
+    if C != 416:
+        raise EngineError("cat must have 416 channels")
+    *_, total = pyramid_layout(T, H4, W4)
+    pyr = torch.empty(total, dtype=torch.float32, device=cat.device)
+    with torch.cuda.device(cat.device):
+        _check(lib().ct3_enc_tail(_ptr(packed), _ptr(cat), T, H4, W4, _ptr(pyr), _ptr(workspace), workspace.numel(),
+                                  _stream(cat.device)), "ct3_enc_tail")
+    return pyr
+
+
+def slice_pyramid(pyr: torch.Tensor, T: int, H4: int, W4: int, t0: int, S: int) -> torch.Tensor:
+    """Frames [t0, t0+S) of every level as a new flat pyramid (sliding-window mode)."""
+    off, h, w, _ = pyramid_layout(T, H4, W4)
+    parts = []
+    for l in range(LEVELS):
+        per = h[l] * w[l] * LATENT
+        parts.append(pyr[off[l] + t0 * per: off[l] + (t0 + S) * per])
+    return torch.cat(parts)

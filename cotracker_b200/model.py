@@ -111,7 +111,10 @@ class CoTrackerThreeBase(nn.Module):
         self.register_buffer("time_emb", sincos_time_embedding(XDIM, window_len))
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
+        self._enc_packed: Optional[torch.Tensor] = None
+        self._enc_key = None
         self._ws = engine.WorkspaceCache()
+        self._enc_ws: Optional[torch.Tensor] = None
 
     # -- engine plumbing ----------------------------------------------------------------------------------
     def _hot_state(self):
@@ -137,14 +140,32 @@ class CoTrackerThreeBase(nn.Module):
         return te[0].contiguous()
 
     def _encode(self, video: torch.Tensor, chunk: int) -> torch.Tensor:
-        """video [T,3,H,W] already scaled to [-1,1] -> raw fnet output [T,128,H/4,W/4] fp32."""
+        """video [T,3,H,W] already scaled to [-1,1] -> L2-normalised channels-last 4-level pyramid (flat fp32).
+
+        Front of the encoder (stem + residual stages + resize/concat, 40 % of its FLOPs): PyTorch/cuDNN fp32 (TF32
+        off).  Tail (conv2 3x3 416->256, InstanceNorm, ReLU, conv3 1x1, L2-normalise, 3x avg-pool): libct3_b200
+        (im2col + cta_group::2 split-bf16x3 GEMMs, csrc/enc_tail.cu).  `chunk` bounds the frames per cuDNN call
+        (reference fmaps_chunk_size)."""
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         try:
-            outs = [self.fnet(video[t:t + chunk]) for t in range(0, video.shape[0], chunk)]
+            outs = [self.fnet.forward_front(video[t:t + chunk]) for t in range(0, video.shape[0], chunk)]
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        return (outs[0] if len(outs) == 1 else torch.cat(outs, 0)).float().contiguous()
+        cat = (outs[0] if len(outs) == 1 else torch.cat(outs, 0)).float().contiguous()
+        dev = cat.device
+        f = self.fnet
+        tail = (f.conv2.weight, f.conv2.bias, f.conv3.weight, f.conv3.bias)
+        key = (str(dev), tuple((v.data_ptr(), v._version) for v in tail))
+        if self._enc_packed is None or self._enc_key != key:
+            self._enc_packed = engine.enc_tail_pack(*tail, dev)
+            self._enc_key = key
+        T, _, H4, W4 = cat.shape
+        need = engine.enc_tail_workspace_bytes(T, H4, W4)
+        if self._enc_ws is None or self._enc_ws.numel() < need or self._enc_ws.device != dev:
+            self._enc_ws = None
+            self._enc_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return engine.enc_tail(self._enc_packed, cat, self._enc_ws)
 
     def _check_inputs(self, video, queries, is_train):
         if is_train:
@@ -174,9 +195,7 @@ class CoTrackerThreeOffline(CoTrackerThreeBase):
         N = queries.shape[1]
         H4, W4 = H // self.stride, W // self.stride
         frames = 2.0 * (video[0].float() / 255.0) - 1.0
-        fmaps = self._encode(frames, fmaps_chunk_size)
-        pyr = engine.prepare_pyramid(fmaps)
-        del fmaps
+        pyr = self._encode(frames, fmaps_chunk_size)
         qframes = queries[0, :, 0].long().to(torch.int32).contiguous()
         qcoords = (queries[0, :, 1:3].float() / self.stride).contiguous()
         support = engine.sample_support(pyr, T, H4, W4, qframes, qcoords)
@@ -229,8 +248,7 @@ class CoTrackerThreeOnline(CoTrackerThreeBase):
             vis_pred = F.pad(self.online_vis_predicted, (0, 0, 0, grow))
             conf_pred = F.pad(self.online_conf_predicted, (0, 0, 0, grow))
 
-        fmaps = self._encode(frames, fmaps_chunk_size if not is_train else T_pad)
-        pyr_all = engine.prepare_pyramid(fmaps)
+        pyr_all = self._encode(frames, fmaps_chunk_size)
 
         # support features of every track at its query frame
         if is_online:
@@ -271,7 +289,7 @@ class CoTrackerThreeOnline(CoTrackerThreeBase):
             if is_online:
                 pyr = pyr_all
             else:
-                pyr = engine.prepare_pyramid(fmaps[ind:ind + S].contiguous())
+                pyr = engine.slice_pyramid(pyr_all, T_pad, H4, W4, ind, S)
             coords = coords_init.clone().contiguous()
             vis = vis_init.clone().contiguous()
             conf = conf_init.clone().contiguous()

@@ -105,6 +105,18 @@ int ct3_sample_support(const float* pyr, int T, int H4, int W4, const int32_t* q
                        const float* queried_coords, int N, const uint8_t* accumulate_mask,
                        float* support, ct3_stream_t stream);
 
+/* ---- encoder tail (partially): conv2 3x3 (416->256) -> InstanceNorm -> ReLU ->
+ * conv3 1x1 (256->128) (BasicEncoder.forward tail, blocks.py:215-218) + L2-normalise + pyramid
+ * (cotracker3_offline.py:92-117) on the GEMM engine.  cat: [T,416,H4,W4] fp32 channel-planar = the concatenated,
+ * bilinearly resized stage outputs (blocks.py:210-215).  Output = the same channels-last pyramid as
+ * ct3_prepare_pyramid.  Weights: conv2.weight [256,416,3,3], conv2.bias, conv3.weight [128,256,1,1], conv3.bias. */
+int ct3_enc_tail_packed_bytes(size_t* out_bytes);
+int ct3_enc_tail_pack(const float* conv2_w, const float* conv2_b, const float* conv3_w, const float* conv3_b,
+                      void* packed, size_t packed_bytes, ct3_stream_t stream);
+int ct3_enc_tail_workspace_bytes(int T, int H4, int W4, size_t* out_bytes);
+int ct3_enc_tail(const void* packed, const float* cat, int T, int H4, int W4, float* pyr, void* workspace,
+                 size_t workspace_bytes, ct3_stream_t stream);
+
 /* ---- the hot loop -----------------------------------------------------------
  * ct3_workspace_bytes: scratch needed by ct3_update_loop / ct3_update_iter. */
 int ct3_workspace_bytes(int T, int N, size_t* out_bytes);

@@ -254,3 +254,30 @@ def test_update_loop_cluster_gemm_vs_simt_at_scale(eng):
     e_v = float((out[0][1] - out[1][1]).abs().max())
     print("cluster-vs-simt", e_c, e_v)
     assert e_c < 5e-4 and e_v < 5e-4
+
+
+def test_encoder_tail_matches_torch(eng):
+    """conv2 -> InstanceNorm -> ReLU -> conv3 -> L2-normalise -> pyramid through the GEMM engine vs fp32 PyTorch on the
+    same GPU (same front features); covers the cta_group::2 path (M = T*H4*W4 rows) and odd map sizes."""
+    from cotracker_b200.build import build_cotracker
+    from cotracker_b200.synthetic import seeded_state_dict, texture_video
+    m = build_cotracker(None, offline=True, window_len=60)
+    m.load_state_dict(seeded_state_dict(5))
+    m = m.to(DEV).eval()
+    for (T, H, W) in [(3, 96, 128), (2, 384, 512), (18, 100, 132)]:
+        x = (2 * (texture_video(T, H, W, seed=T)[0] / 255) - 1).to(DEV)
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                want_fm = m.fnet(x)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        want = O.normalized_pyramid(want_fm.cpu())
+        with torch.no_grad():
+            pyr = m._encode(x, 200)
+        levels = eng.pyramid_levels(pyr, T, H // 4, W // 4)
+        for l in range(4):
+            got = levels[l].permute(0, 3, 1, 2).cpu()
+            err = float((got - want[l]).abs().max())
+            assert err < 2e-5, (T, H, W, l, err)     # unit-norm features: 2e-5 abs ~ bf16x3 + fp32 ordering noise
