@@ -336,3 +336,15 @@ def slice_pyramid(pyr: torch.Tensor, T: int, H4: int, W4: int, t0: int, S: int) 
         per = h[l] * w[l] * LATENT
         parts.append(pyr[off[l] + t0 * per: off[l] + (t0 + S) * per])
     return torch.cat(parts)
+
+
+def concat_pyramid_frames(pyr_a: torch.Tensor, Ta: int, a0: int, pyr_b: torch.Tensor, Tb: int, H4: int, W4: int):
+    """Flat pyramid holding frames [a0, Ta) of `pyr_a` followed by all Tb frames of `pyr_b` (online feature reuse)."""
+    off_a, h, w, _ = pyramid_layout(Ta, H4, W4)
+    off_b, _, _, _ = pyramid_layout(Tb, H4, W4)
+    parts = []
+    for l in range(LEVELS):
+        per = h[l] * w[l] * LATENT
+        parts.append(pyr_a[off_a[l] + a0 * per: off_a[l] + Ta * per])
+        parts.append(pyr_b[off_b[l]: off_b[l] + Tb * per])
+    return torch.cat(parts)

@@ -133,11 +133,14 @@ class CoTrackerThreeBase(nn.Module):
         return self._packed
 
     def interpolate_time_embed(self, t: int) -> torch.Tensor:
-        """[t, 1110] time embedding (reference cotracker3_online.py:145-156)."""
-        te = self.time_emb.float()
-        if t != te.shape[1]:
-            te = F.interpolate(te.permute(0, 2, 1), size=t, mode="linear").permute(0, 2, 1)
-        return te[0].contiguous()
+        """[t, 1110] time embedding (reference cotracker3_online.py:145-156); constant per (buffer, t): cached."""
+        key = (t, self.time_emb.data_ptr(), self.time_emb._version, str(self.time_emb.device))
+        if getattr(self, "_te_key", None) != key:
+            te = self.time_emb.float()
+            if t != te.shape[1]:
+                te = F.interpolate(te.permute(0, 2, 1), size=t, mode="linear").permute(0, 2, 1)
+            self._te_cache, self._te_key = te[0].contiguous(), key
+        return self._te_cache
 
     def _encode(self, video: torch.Tensor, chunk: int) -> torch.Tensor:
         """video [T,3,H,W] already scaled to [-1,1] -> L2-normalised channels-last 4-level pyramid (flat fp32).
@@ -215,6 +218,25 @@ class CoTrackerThreeOnline(CoTrackerThreeBase):
         self.online_coords_predicted = None
         self.online_vis_predicted = None
         self.online_conf_predicted = None
+        self._online_enc_cache = None             # (frames, pyramid) of the previous chunk
+
+    def _encode_online(self, frames, chunk, step, H4, W4):
+        """Consecutive online chunks overlap by window_len - step frames and the encoder is strictly per-frame
+        (InstanceNorm statistics are per sample), so the features of the overlap are reused bit-for-bit from the
+        previous call and only the new frames are encoded (the reference re-encodes all 16)."""
+        S = frames.shape[0]
+        keep = S - step
+        cache = getattr(self, "_online_enc_cache", None)
+        pyr = None
+        if cache is not None and self.online_ind > 0 and keep > 0:
+            prev_frames, prev_pyr = cache
+            if prev_frames.shape == frames.shape and torch.equal(frames[:keep], prev_frames[step:]):
+                new = self._encode(frames[keep:].contiguous(), chunk)
+                pyr = engine.concat_pyramid_frames(prev_pyr, S, step, new, S - keep, H4, W4)
+        if pyr is None:
+            pyr = self._encode(frames, chunk)
+        self._online_enc_cache = (frames, pyr)
+        return pyr
 
     @torch.no_grad()
     def forward(self, video, queries, iters=4, is_train=False, add_space_attn=True, fmaps_chunk_size=200,
@@ -248,7 +270,8 @@ class CoTrackerThreeOnline(CoTrackerThreeBase):
             vis_pred = F.pad(self.online_vis_predicted, (0, 0, 0, grow))
             conf_pred = F.pad(self.online_conf_predicted, (0, 0, 0, grow))
 
-        pyr_all = self._encode(frames, fmaps_chunk_size)
+        pyr_all = self._encode_online(frames, fmaps_chunk_size, step, H4, W4) if is_online \
+            else self._encode(frames, fmaps_chunk_size)
 
         # support features of every track at its query frame
         if is_online:
