@@ -663,6 +663,19 @@ int ct3_enc_tail_pack(const float* conv2_w, const float* conv2_b, const float* c
   return 0;
 }
 
+int ct3_upsample_concat(const float* const* src, const int* channels, const int* heights, const int* widths, int T,
+                        int H, int W, float* out, ct3_stream_t stream) {
+  if (!src || !channels || !heights || !widths || !out) return fail(CT3_EINVAL, "null argument%s");
+  int ctot = 0;
+  for (int k = 0; k < 4; ++k) {
+    if (!src[k] || channels[k] < 1 || heights[k] < 1 || widths[k] < 1) return fail(CT3_EINVAL, "bad stage tensor%s");
+    ctot += channels[k];
+  }
+  if (T < 1 || H < 1 || W < 1) return fail(CT3_EINVAL, "bad output shape%s");
+  CK(launch_upsample_concat(src, channels, heights, widths, T, H, W, out, (cudaStream_t)stream), "upsample_concat");
+  return 0;
+}
+
 int ct3_enc_tail_workspace_bytes(int T, int H4, int W4, size_t* out_bytes) {
   if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
   if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;

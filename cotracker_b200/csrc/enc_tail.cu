@@ -109,7 +109,56 @@ l2norm_rows_kernel(const float* __restrict__ in, int64_t rows, float* __restrict
   reinterpret_cast<float4*>(out + row * kD)[lane] = make_float4(v.x / d, v.y / d, v.z / d, v.w / d);
 }
 
+// bilinear (align_corners=True) resize of 4 stage outputs [T,Cs,Hs,Ws] to (H,W) + channel concat -> [T,416,H,W]
+// (BasicEncoder._bilinear_intepolate + torch.cat, blocks.py:202-215).  One thread = one output pixel of one channel.
+struct UpArgs {
+  const float* src[4];
+  int c[4], h[4], w[4], coff[4];
+};
+__global__ void upsample_concat_kernel(UpArgs a, int T, int Ctot, int H, int W, float* __restrict__ out) {
+  const int64_t total = (int64_t)T * Ctot * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    int64_t r = i / W;
+    const int y = (int)(r % H);
+    r /= H;
+    const int cc = (int)(r % Ctot);
+    const int t = (int)(r / Ctot);
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) s = (cc >= a.coff[k]) ? k : s;
+    const int c = cc - a.coff[s], hs = a.h[s], ws = a.w[s];
+    const float* p = a.src[s] + ((int64_t)t * a.c[s] + c) * hs * ws;
+    float v;
+    if (hs == H && ws == W) {
+      v = p[(int64_t)y * ws + x];
+    } else {
+      // area_pixel_compute_source_index(align_corners): src = dst * (in - 1) / (out - 1)
+      const float sy = H > 1 ? (float)(hs - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(ws - 1) / (float)(W - 1) : 0.f;
+      const float fy = sy * (float)y, fx = sx * (float)x;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+      const float ly = fy - (float)y0, lx = fx - (float)x0;
+      const float v00 = p[(int64_t)y0 * ws + x0], v01 = p[(int64_t)y0 * ws + x1];
+      const float v10 = p[(int64_t)y1 * ws + x0], v11 = p[(int64_t)y1 * ws + x1];
+      v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    }
+    out[i] = v;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_upsample_concat(const float* const src[4], const int c[4], const int h[4], const int w[4], int T,
+                                   int H, int W, float* out, cudaStream_t s) {
+  UpArgs a;
+  int off = 0;
+  for (int k = 0; k < 4; ++k) { a.src[k] = src[k]; a.c[k] = c[k]; a.h[k] = h[k]; a.w[k] = w[k]; a.coff[k] = off; off += c[k]; }
+  const int64_t total = (int64_t)T * off * H * W;
+  const int blocks = (int)((total + 255) / 256 > 148 * 64 ? 148 * 64 : (total + 255) / 256);
+  upsample_concat_kernel<<<blocks, 256, 0, s>>>(a, T, off, H, W, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_im2col3x3_split(const float* in, int T, int C, int H, int W, int Kpad, __nv_bfloat16* out,
                                    cudaStream_t s) {

@@ -26,6 +26,8 @@ cudaError_t launch_instnorm_stats(const float* y, int T, int HW, int C, float ep
 cudaError_t launch_instnorm_relu_split(const float* y, const float* stats, int64_t rows, int HW, int C,
                                        __nv_bfloat16* out, cudaStream_t s);
 cudaError_t launch_l2norm_rows(const float* in, int64_t rows, float* out, cudaStream_t s);
+cudaError_t launch_upsample_concat(const float* const src[4], const int c[4], const int h[4], const int w[4], int T,
+                                   int H, int W, float* out, cudaStream_t s);
 
 // ---- corr.cu : correlation sampling ---------------------------------------------------------------
 // vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level

@@ -54,16 +54,20 @@ class BasicEncoder(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
-    def forward_front(self, x):
-        """Stem + four residual stages + resize + concat -> [T, 416, H/4, W/4] (the input of conv2)."""
-        H, W = x.shape[-2:]
-        size = (H // self.stride, W // self.stride)
+    def stages(self, x):
+        """Stem + four residual stages -> their 4 outputs (64@1/2, 96@1/4, 128@1/8, 128@1/16 of the input)."""
         x = F.relu(F.instance_norm(self.conv1(x)))
         feats = []
         for i in range(1, 5):
             x = getattr(self, f"layer{i}")(x)
-            feats.append(F.interpolate(x, size, mode="bilinear", align_corners=True))
-        return torch.cat(feats, dim=1)
+            feats.append(x)
+        return feats
+
+    def forward_front(self, x):
+        """Stages + bilinear resize (align_corners) + concat -> [T, 416, H/4, W/4] (the input of conv2), PyTorch."""
+        H, W = x.shape[-2:]
+        size = (H // self.stride, W // self.stride)
+        return torch.cat([F.interpolate(f, size, mode="bilinear", align_corners=True) for f in self.stages(x)], dim=1)
 
     def forward(self, x):
         x = F.relu(F.instance_norm(self.conv2(self.forward_front(x))))

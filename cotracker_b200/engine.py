@@ -48,6 +48,7 @@ def _declare(lib):
         "ct3_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_split_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_updateformer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "ct3_upsample_concat": (c_int, [ctypes.POINTER(c_void_p), intp, intp, intp, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_enc_tail_packed_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
         "ct3_enc_tail_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
         "ct3_enc_tail_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
@@ -67,7 +68,7 @@ EXPORTED_SYMBOLS = [
     "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
     "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
     "ct3_corr_sample", "ct3_linear", "ct3_split_rows", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
-    "ct3_enc_tail_packed_bytes", "ct3_enc_tail_pack", "ct3_enc_tail_workspace_bytes", "ct3_enc_tail",
+    "ct3_upsample_concat", "ct3_enc_tail_packed_bytes", "ct3_enc_tail_pack", "ct3_enc_tail_workspace_bytes", "ct3_enc_tail",
 ]
 
 
@@ -348,3 +349,19 @@ def concat_pyramid_frames(pyr_a: torch.Tensor, Ta: int, a0: int, pyr_b: torch.Te
         parts.append(pyr_a[off_a[l] + a0 * per: off_a[l] + Ta * per])
         parts.append(pyr_b[off_b[l]: off_b[l] + Tb * per])
     return torch.cat(parts)
+
+
+def upsample_concat(feats: Sequence[torch.Tensor], H: int, W: int) -> torch.Tensor:
+    """4 stage outputs [T,Cs,Hs,Ws] -> bilinear(align_corners=True) to HxW, concatenated on channels [T,sum Cs,H,W]."""
+    if len(feats) != 4:
+        raise EngineError("upsample_concat expects 4 stage tensors")
+    fs = [_req(f, torch.float32, "stage feature") for f in feats]
+    T = fs[0].shape[0]
+    out = torch.empty(T, sum(f.shape[1] for f in fs), H, W, dtype=torch.float32, device=fs[0].device)
+    src = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in fs])
+    ch = (ctypes.c_int * 4)(*[f.shape[1] for f in fs])
+    hh = (ctypes.c_int * 4)(*[f.shape[2] for f in fs])
+    ww = (ctypes.c_int * 4)(*[f.shape[3] for f in fs])
+    with torch.cuda.device(out.device):
+        _check(lib().ct3_upsample_concat(src, ch, hh, ww, T, H, W, _ptr(out), _stream(out.device)), "ct3_upsample_concat")
+    return out

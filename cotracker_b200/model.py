@@ -152,10 +152,14 @@ class CoTrackerThreeBase(nn.Module):
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         try:
-            outs = [self.fnet.forward_front(video[t:t + chunk]) for t in range(0, video.shape[0], chunk)]
+            H4, W4 = video.shape[-2] // self.stride, video.shape[-1] // self.stride
+            outs = []
+            for t in range(0, video.shape[0], chunk):
+                feats = [f.float().contiguous() for f in self.fnet.stages(video[t:t + chunk])]
+                outs.append(engine.upsample_concat(feats, H4, W4))   # fused resize + concat (csrc/enc_tail.cu)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        cat = (outs[0] if len(outs) == 1 else torch.cat(outs, 0)).float().contiguous()
+        cat = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         dev = cat.device
         f = self.fnet
         tail = (f.conv2.weight, f.conv2.bias, f.conv3.weight, f.conv3.bias)

@@ -110,6 +110,10 @@ int ct3_sample_support(const float* pyr, int T, int H4, int W4, const int32_t* q
  * (cotracker3_offline.py:92-117) on the GEMM engine.  cat: [T,416,H4,W4] fp32 channel-planar = the concatenated,
  * bilinearly resized stage outputs (blocks.py:210-215).  Output = the same channels-last pyramid as
  * ct3_prepare_pyramid.  Weights: conv2.weight [256,416,3,3], conv2.bias, conv3.weight [128,256,1,1], conv3.bias. */
+/* bilinear (align_corners=True) resize of the 4 stage outputs [T,Cs,Hs,Ws] (fp32, planar) to H x W and channel concat
+ * -> out [T, sum Cs, H, W] (blocks.py:202-215); src/channels/heights/widths are HOST arrays of 4 entries. */
+int ct3_upsample_concat(const float* const* src, const int* channels, const int* heights, const int* widths, int T,
+                        int H, int W, float* out, ct3_stream_t stream);
 int ct3_enc_tail_packed_bytes(size_t* out_bytes);
 int ct3_enc_tail_pack(const float* conv2_w, const float* conv2_b, const float* conv3_w, const float* conv3_b,
                       void* packed, size_t packed_bytes, ct3_stream_t stream);

@@ -281,3 +281,15 @@ def test_encoder_tail_matches_torch(eng):
             got = levels[l].permute(0, 3, 1, 2).cpu()
             err = float((got - want[l]).abs().max())
             assert err < 2e-5, (T, H, W, l, err)     # unit-norm features: 2e-5 abs ~ bf16x3 + fp32 ordering noise
+
+
+def test_upsample_concat_matches_torch(eng):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(8)
+    for (T, H, W) in [(2, 24, 32), (3, 25, 33), (1, 96, 128)]:
+        shapes = [(64, 2 * H, 2 * W), (96, H, W), (128, (H + 1) // 2, (W + 1) // 2), (128, (H + 3) // 4, (W + 3) // 4)]
+        feats = [torch.randn(T, c, h, w, generator=g).to(DEV) for (c, h, w) in shapes]
+        want = torch.cat([F.interpolate(f, (H, W), mode="bilinear", align_corners=True) for f in feats], dim=1)
+        got = eng.upsample_concat(feats, H, W)
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) < 2e-5
