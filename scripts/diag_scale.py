@@ -19,9 +19,8 @@ def sync_time(fn):
     torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); return r, (time.perf_counter() - t0) * 1e3
 
 frames = 2.0 * (video[0] / 255.0) - 1.0
-fm, ms = sync_time(lambda: m._encode(frames, 200)); print(f"fnet {ms:.1f} ms", flush=True)
-fm, ms = sync_time(lambda: m._encode(frames, 200)); print(f"fnet(2) {ms:.1f} ms", flush=True)
-pyr, ms = sync_time(lambda: engine.prepare_pyramid(fm)); print(f"pyramid {ms:.2f} ms", flush=True)
+pyr, ms = sync_time(lambda: m._encode(frames, 200)); print(f"encoder+pyramid {ms:.1f} ms", flush=True)
+pyr, ms = sync_time(lambda: m._encode(frames, 200)); print(f"encoder+pyramid(2) {ms:.1f} ms", flush=True)
 for G in grids:
     N = G * G
     pts = get_points_on_a_grid(G, (384, 512), device=dev)[0]
