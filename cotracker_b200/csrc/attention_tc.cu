@@ -30,7 +30,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 template <int KB, bool PER_WARP>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 4)
 attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, int qtw, float* part_ml, float* part_o) {
   constexpr int VPAD = KB + 8;  // bf16 row stride of V^T tiles
   constexpr int SLICE = 2 * KB * KPAD + 2 * kDh * VPAD;  // bf16 elements per K/V staging slice
@@ -328,10 +328,15 @@ cudaError_t launch_attention_tc(const AttnParams& p, bool per_warp, float* part,
   const int chunks = (p.Lk + 63) / 64;
   int splits = 1;
   if (part != nullptr && ctas < 2 * num_sms && chunks >= 8) {
-    splits = (4 * num_sms + ctas - 1) / ctas;
-    if (splits > kAttnMaxSplits) splits = kAttnMaxSplits;
-    if (splits > chunks / 2) splits = chunks / 2;
-    if (splits < 1) splits = 1;
+    // split-K so that the grid fills whole waves of the 4-CTA/SM occupancy: minimise waves x chunks-per-split
+    const int slots = 4 * num_sms;
+    long long best = -1;
+    const int smax = kAttnMaxSplits < chunks / 2 ? kAttnMaxSplits : chunks / 2;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long waves = ((long long)ctas * sp + slots - 1) / slots;
+      const long long cost = waves * ((chunks + sp - 1) / sp);
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
   }
   if (splits == 1) {
     // K/V of one chunk are staged once per CTA: amortise the conversion over several query tiles per warp while
