@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libct3_b200.so")
+LIB_PATH = os.environ.get("CT3_B200_LIB", os.path.join(_HERE, "lib", "libct3_b200.so"))   # env override: A/B builds
 
 LATENT, LEVELS, P, VOL, VOL_PAD = 128, 4, 49, 2401, 2432
 HID, VIRT, XDIM, XDIM_PAD = 384, 64, 1110, 1152
