@@ -41,9 +41,8 @@ constexpr int OFF_S = 0;
 constexpr int OFF_A = OFF_S + S_BYTES;
 constexpr int OFF_PATCH = OFF_A + A_BYTES;
 constexpr int OFF_STG = OFF_PATCH + NPATCH * PATCH_BYTES;
-constexpr int PARAM_WORDS = 48;                     // per slot: box_x, box_y, pad, pad, then x0[7] x1[7] wx[7] y0[7] y1[7] wy[7] (+2 pad)
-constexpr int OFF_PARAM = OFF_STG + STG_BYTES;
-constexpr int OFF_BAR = OFF_PARAM + NPATCH * PARAM_WORDS * 4;
+constexpr int OFF_PARAM = OFF_STG + STG_BYTES;      // NPATCH x {cx, cy, box_x, box_y}
+constexpr int OFF_BAR = OFF_PARAM + NPATCH * 16;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr uint32_t TMEM_COLS = 128;       // 2 accumulators x 64 columns
@@ -164,20 +163,25 @@ corr_sample_tc_kernel(const __grid_constant__ CorrTcArgs g, const __grid_constan
           const uint32_t fr = fc + f;                  // frame sequence number -> ring slot
           const int slot = fr % NPATCH;
           mbar_wait(&p_full[slot], (fr / NPATCH) & 1u);
-          const int* prm = reinterpret_cast<const int*>(smem + OFF_PARAM) + slot * PARAM_WORDS;
-          const int bx = prm[0], by = prm[1];
+          const float4 prm = *reinterpret_cast<const float4*>(smem + OFF_PARAM + slot * 16);
+          const float cx = prm.x, cy = prm.y;
+          const int bx = __float_as_int(prm.z), by = __float_as_int(prm.w);
           const float* patch = reinterpret_cast<const float*>(smem + OFF_PATCH + slot * PATCH_BYTES) + lane * 4;
-          const int x0 = prm[4 + a], x1 = prm[11 + a];
-          const float wx = __int_as_float(prm[18 + a]);
+          const float x = fminf(fmaxf(cx + (float)(a - kR), 0.f), (float)(W - 1));
+          const float xf = floorf(x);
+          const int x0 = (int)xf, x1 = min(x0 + 1, W - 1);
+          const float wx = x - xf;
           float wy[7];
           int y0[7], yl[8];   // yl[0] = y0 of sample 0, yl[k+1] = y1 of sample k: the (<= 8) distinct rows of the column
 #pragma unroll
           for (int b = 0; b < 7; ++b) {
-            y0[b] = prm[25 + b];
-            yl[b + 1] = prm[32 + b];
-            wy[b] = __int_as_float(prm[39 + b]);
+            const float y = fminf(fmaxf(cy + (float)(b - kR), 0.f), (float)(H - 1));
+            const float yf = floorf(y);
+            y0[b] = (int)yf;
+            wy[b] = y - yf;
+            if (b == 0) yl[0] = y0[0];
+            yl[b + 1] = min(y0[b] + 1, H - 1);
           }
-          yl[0] = y0[0];
           // fast path (always, bar fp32 corner cases of floor(c + offset)): every tap of the column is in the box
           // and each sample's upper row is either the previous sample's lower row or (low-border clamp) row yl[0]
           bool fast = (x0 >= bx) && (x1 < bx + bw) && (yl[0] >= by) && (yl[7] < by + bh);
@@ -192,21 +196,13 @@ corr_sample_tc_kernel(const __grid_constant__ CorrTcArgs g, const __grid_constan
               const int ro = (yl[k] - by) * bw * kD;
               hrow[k] = lerp4(*reinterpret_cast<const float4*>(pa + ro), *reinterpret_cast<const float4*>(pb + ro), wx);
             }
-            bool consecutive = true;
 #pragma unroll
-            for (int b = 1; b < 7; ++b) consecutive = consecutive && (y0[b] == yl[b]);
-            if (consecutive) {   // no sample clamped at the low border: sample b blends rows b and b+1
-#pragma unroll
-              for (int b = 0; b < 7; ++b) outv[b] = lerp4(hrow[b], hrow[b + 1], wy[b]);
-            } else {
-#pragma unroll
-              for (int b = 0; b < 7; ++b) {
-                const bool same = (y0[b] == yl[b]);
-                float4 h0;
-                h0.x = same ? hrow[b].x : hrow[0].x; h0.y = same ? hrow[b].y : hrow[0].y;
-                h0.z = same ? hrow[b].z : hrow[0].z; h0.w = same ? hrow[b].w : hrow[0].w;
-                outv[b] = lerp4(h0, hrow[b + 1], wy[b]);
-              }
+            for (int b = 0; b < 7; ++b) {
+              const bool same = (y0[b] == yl[b]);
+              float4 h0;
+              h0.x = same ? hrow[b].x : hrow[0].x; h0.y = same ? hrow[b].y : hrow[0].y;
+              h0.z = same ? hrow[b].z : hrow[0].z; h0.w = same ? hrow[b].w : hrow[0].w;
+              outv[b] = lerp4(h0, hrow[b + 1], wy[b]);
             }
           } else {
             const float* fm = g.pyr + g.lay.off[l] + (int64_t)t * H * W * kD + lane * 4;
@@ -256,28 +252,12 @@ corr_sample_tc_kernel(const __grid_constant__ CorrTcArgs g, const __grid_constan
         for (int k = 0; k < cnt; ++k, ++fc) {
           const float cx = __shfl_sync(0xffffffffu, c.x, k) * inv;
           const float cy = __shfl_sync(0xffffffffu, c.y, k) * inv;
-          const int slot = fc % NPATCH;
-          if (lane == 0) mbar_wait(&p_empty[slot], ((fc / NPATCH) & 1u) ^ 1u);
-          __syncwarp();                                   // slot (and its parameter block) is free
-          const int bx = box_origin(cx, W), by = box_origin(cy, H);
-          uint32_t* prm = reinterpret_cast<uint32_t*>(smem + OFF_PARAM) + slot * PARAM_WORDS;
-          if (lane < 7) {
-            // tap indices / weights of x-offset (lane-3) and y-offset (lane-3): computed once per frame here instead
-            // of by each of the 7 sampler warps
-            const float x = fminf(fmaxf(cx + (float)(lane - kR), 0.f), (float)(W - 1));
-            const float y = fminf(fmaxf(cy + (float)(lane - kR), 0.f), (float)(H - 1));
-            const float xf = floorf(x), yf = floorf(y);
-            prm[4 + lane] = (uint32_t)(int)xf;
-            prm[11 + lane] = (uint32_t)min((int)xf + 1, W - 1);
-            prm[18 + lane] = __float_as_uint(x - xf);
-            prm[25 + lane] = (uint32_t)(int)yf;
-            prm[32 + lane] = (uint32_t)min((int)yf + 1, H - 1);
-            prm[39 + lane] = __float_as_uint(y - yf);
-          }
-          if (lane == 0) { prm[0] = (uint32_t)bx; prm[1] = (uint32_t)by; }
-          __threadfence_block();
-          __syncwarp();
           if (lane == 0) {
+            const int slot = fc % NPATCH;
+            mbar_wait(&p_empty[slot], ((fc / NPATCH) & 1u) ^ 1u);
+            const int bx = box_origin(cx, W), by = box_origin(cy, H);
+            *reinterpret_cast<float4*>(smem + OFF_PARAM + slot * 16) =
+                make_float4(cx, cy, __int_as_float(bx), __int_as_float(by));
             mbar_arrive_expect_tx(&p_full[slot], (uint32_t)(min(W, 8) * min(H, 8) * kD * 4));
             tma_load_4d(smem + OFF_PATCH + slot * PATCH_BYTES, &maps.m[l], 0, bx, by, t0 + k, &p_full[slot]);
           }
