@@ -106,25 +106,37 @@ attention_tc_kernel(AttnParams p, int q_tiles, int num_splits, int qtw, float* p
     if (stage_now) {
       const int nthr = PER_WARP ? 32 : WARPS * 32;
       const int tid = PER_WARP ? lane : threadIdx.x;
-      for (int idx = tid; idx < KB * (kDh / 4); idx += nthr) {
-        const int j = idx / (kDh / 4), d4 = idx % (kDh / 4);
-        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      // one work item = 4 channels of two adjacent keys: K rows get 8-byte stores, V^T gets 4-byte stores of
+      // (key j, key j+1) pairs instead of 2-byte scatters
+      for (int idx = tid; idx < (KB / 2) * (kDh / 4); idx += nthr) {
+        const int j = 2 * (idx / (kDh / 4)), d4 = idx % (kDh / 4);
+        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, v0 = k0, v1 = k0;
         if (kc0 + j < p.Lk) {
           const float* base = p.kv + ((int64_t)s * p.k_seq_stride + (int64_t)(kc0 + j) * p.k_tok_stride) * p.kv_ld + h * kDh;
-          kv = __ldg(reinterpret_cast<const float4*>(base + p.k_col) + d4);
-          vv = __ldg(reinterpret_cast<const float4*>(base + p.v_col) + d4);
+          k0 = __ldg(reinterpret_cast<const float4*>(base + p.k_col) + d4);
+          v0 = __ldg(reinterpret_cast<const float4*>(base + p.v_col) + d4);
+        }
+        if (kc0 + j + 1 < p.Lk) {
+          const float* base = p.kv + ((int64_t)s * p.k_seq_stride + (int64_t)(kc0 + j + 1) * p.k_tok_stride) * p.kv_ld + h * kDh;
+          k1 = __ldg(reinterpret_cast<const float4*>(base + p.k_col) + d4);
+          v1 = __ldg(reinterpret_cast<const float4*>(base + p.v_col) + d4);
         }
         uint32_t h0, l0_, h1, l1_;
-        split2(kv.x, kv.y, h0, l0_);
-        split2(kv.z, kv.w, h1, l1_);
+        split2(k0.x, k0.y, h0, l0_);
+        split2(k0.z, k0.w, h1, l1_);
         *reinterpret_cast<uint2*>(Kh + j * KPAD + 4 * d4) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(Kl + j * KPAD + 4 * d4) = make_uint2(l0_, l1_);
-        const float vs[4] = {vv.x, vv.y, vv.z, vv.w};
+        split2(k1.x, k1.y, h0, l0_);
+        split2(k1.z, k1.w, h1, l1_);
+        *reinterpret_cast<uint2*>(Kh + (j + 1) * KPAD + 4 * d4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(Kl + (j + 1) * KPAD + 4 * d4) = make_uint2(l0_, l1_);
+        const float va[4] = {v0.x, v0.y, v0.z, v0.w}, vb[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const bf16pair pr = split_bf16(vs[i]);
-          Vh[(4 * d4 + i) * VPAD + j] = pr.hi;
-          Vl[(4 * d4 + i) * VPAD + j] = pr.lo;
+          uint32_t vh, vl;
+          split2(va[i], vb[i], vh, vl);   // (key j | key j+1) of channel 4*d4+i
+          *reinterpret_cast<uint32_t*>(Vh + (4 * d4 + i) * VPAD + j) = vh;
+          *reinterpret_cast<uint32_t*>(Vl + (4 * d4 + i) * VPAD + j) = vl;
         }
       }
     }
