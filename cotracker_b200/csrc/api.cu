@@ -173,9 +173,10 @@ struct Workspace {
   __nv_bfloat16* hmid;    // [(N+64)*T, 2*1536]
   float* row_bias;        // [T, 384]
   float* att_part;        // split-K partials of the virtual<-point attention
+  __nv_bfloat16* pyr_split;  // split-bf16 copy of the pyramid (corr_tc2.cu); null when H4 == 0
   size_t total;
 };
-Workspace carve(void* base, int T, int N) {
+Workspace carve(void* base, int T, int N, int H4 = 0, int W4 = 0) {
   Workspace w;
   const size_t R = (size_t)(N + kV) * T, Rp = (size_t)N * T, Rv = (size_t)kV * T, Mc = Rp * kL;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
@@ -192,6 +193,9 @@ Workspace carve(void* base, int T, int N) {
   w.hmid = (__nv_bfloat16*)take(R * 2 * kMlpHid * 2);
   w.row_bias = (float*)take((size_t)T * kC * 4);
   w.att_part = (float*)take(attention_partial_bytes(T, kV, kAttnMaxSplits));
+  w.pyr_split = nullptr;
+  if (H4 > 0 && W4 > 0 && corr_patch_supported(T, H4, W4))
+    w.pyr_split = (__nv_bfloat16*)take((size_t)pyramid_layout(T, H4, W4).total * 4);
   w.total = off;
   return w;
 }
@@ -495,20 +499,30 @@ int ct3_profile_read(double* ms, int* launches, double* gemm_flops) {
   return 0;
 }
 
-int ct3_workspace_bytes(int T, int N, size_t* out_bytes) {
+int ct3_workspace_bytes(int T, int N, int H4, int W4, size_t* out_bytes) {
   if (!out_bytes) return fail(CT3_EINVAL, "null out_bytes%s");
   if (int rc = check_TN(T, N)) return rc;
-  *out_bytes = carve(nullptr, T, N).total;
+  if ((H4 != 0 || W4 != 0))
+    if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  *out_bytes = carve(nullptr, T, N, H4, W4).total;
   return 0;
 }
 
 int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support, const uint8_t* track_valid,
-                    const float* coords, int T, int N, void* vol_split, ct3_stream_t stream) {
+                    const float* coords, int T, int N, void* vol_split, void* scratch, size_t scratch_bytes,
+                    ct3_stream_t stream) {
   if (!pyr || !support || !coords || !vol_split) return fail(CT3_EINVAL, "null argument%s");
   if (int rc = check_TN(T, N)) return rc;
   if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
-  CK(launch_corr_sample(pyr, H4, W4, support, track_valid, coords, T, N, (__nv_bfloat16*)vol_split, g_opt_corr,
-                        num_sms(), (cudaStream_t)stream), "corr_sample");
+  const __nv_bfloat16* pyr_split = nullptr;
+  if (scratch && g_opt_corr == 0 && corr_patch_supported(T, H4, W4)) {
+    if ((uintptr_t)scratch & 255) return fail(CT3_EINVAL, "scratch must be 256-byte aligned%s");
+    if (scratch_bytes < (size_t)pyramid_layout(T, H4, W4).total * 4) return fail(CT3_ENOSPC, "scratch too small%s");
+    CK(launch_split_pyramid(pyr, T, H4, W4, (__nv_bfloat16*)scratch, (cudaStream_t)stream), "split_pyramid");
+    pyr_split = (const __nv_bfloat16*)scratch;
+  }
+  CK(launch_corr_sample(pyr, pyr_split, H4, W4, support, track_valid, coords, T, N, (__nv_bfloat16*)vol_split,
+                        g_opt_corr, num_sms(), (cudaStream_t)stream), "corr_sample");
   return 0;
 }
 
@@ -549,19 +563,23 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
   if (iters < 0) return fail(CT3_EINVAL, "iters must be >= 0%s");
   if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
   if ((uintptr_t)workspace & 255) return fail(CT3_EINVAL, "workspace must be 256-byte aligned%s");
-  const Workspace W = carve(workspace, T, N);
+  const Workspace W = carve(workspace, T, N, H4, W4);
   if (workspace_bytes < W.total) return fail(CT3_ENOSPC, "workspace too small%s");
   const Layout& L = layout();
   Runner R{reinterpret_cast<const uint8_t*>(packed), L, (cudaStream_t)stream, g_opt_gemm};
   const uint8_t* pk = R.pk;
   const int Rp = N * T, Mc = Rp * kL;
+  // split-bf16 copy of the window's pyramid: the TMA source of the correlation kernel, made once per call
+  const __nv_bfloat16* pyr_split = (g_opt_corr == 0 && iters > 0) ? W.pyr_split : nullptr;
+  if (pyr_split) RUNC(CAT_MISC, launch_split_pyramid(pyr, T, H4, W4, W.pyr_split, R.s));
 
   // W_in * time_emb[t]: x + time_emb is folded into a per-frame bias of input_transform (cotracker3_offline.py:196)
   RUNC(CAT_MISC, launch_row_bias(time_emb, reinterpret_cast<const float*>(pk + L.win_f32), T, W.row_bias, R.s));
 
   for (int it = 0; it < iters; ++it) {
     // (i)+(ii) sampling + 4-D correlation, all levels -> split volume
-    RUNC(CAT_CORR, launch_corr_sample(pyr, H4, W4, support, track_valid, coords, T, N, W.vol, g_opt_corr, num_sms(), R.s));
+    RUNC(CAT_CORR, launch_corr_sample(pyr, pyr_split, H4, W4, support, track_valid, coords, T, N, W.vol, g_opt_corr,
+                                      num_sms(), R.s));
     // (iii) corr_mlp: 2401 -> 384 (GELU erf) -> 256, written straight into X columns [256*l, 256*l+256)
     RUNC(-1, R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
     {

@@ -121,10 +121,12 @@ corr_sample_simt_kernel(CorrArgs g) {
 
 }  // namespace
 
-cudaError_t launch_corr_sample(const float* pyr, int H4, int W4, const float* support,
+cudaError_t launch_corr_sample(const float* pyr, const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                const uint8_t* track_valid, const float* coords, int T, int N,
                                __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s) {
-  if (impl == 0) return launch_corr_sample_tc(pyr, H4, W4, support, track_valid, coords, T, N, vol_split, num_sms, s);
+  if (impl == 0 && pyr_split != nullptr && corr_patch_supported(T, H4, W4))
+    return launch_corr_patch_tc(pyr_split, H4, W4, support, track_valid, coords, T, N, vol_split, num_sms, s);
+  if (impl != 1) return launch_corr_sample_tc(pyr, H4, W4, support, track_valid, coords, T, N, vol_split, num_sms, s);
   CorrArgs g;  // impl 1: exact-fp32 SIMT verification kernel
   g.pyr = pyr;
   g.lay = pyramid_layout(T, H4, W4);

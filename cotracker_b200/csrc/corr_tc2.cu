@@ -1,0 +1,383 @@
+// corr_tc2.cu -- correlate-then-interpolate form of the fused sampling + 4-D correlation (production path when
+// every pyramid level is at least 8x8 texels; corr_tc.cu covers smaller maps, corr.cu is the fp32 SIMT check).
+//
+//   vol[(n,t,l)][(a*7+b)*49 + k] = < bilinear(F_l[t], cx/2^l + a-3, cy/2^l + b-3) , S_l[n, k, :] >
+//   (get_correlation_feat + einsum, cotracker3_online.py:130-143, cotracker3_offline.py:144-156)
+//
+// Bilinear sampling is linear in the feature map, so the 49 sampled vectors never have to exist:
+//   < sum_j w_j F[p_j] , S_k >  =  sum_j w_j < F[p_j] , S_k >.
+// The tensor cores correlate the RAW 8x8 texel patch around the track with the 49 support vectors, and the
+// epilogue blends the 64 raw correlations into the 49 sampled ones (separable, border clamp per sample exactly as
+// grid_sample(padding_mode="border") does).  What this removes from the per-frame shared-memory budget of
+// corr_tc.cu: the fp32 patch reads of the samplers, the split-bf16 A-tile writes, and the output staging image.
+//
+//   pyramid : a split-bf16 copy [level][plane hi|lo][T][H][W][128] made once per update-loop call
+//   A tile  [128 x 128] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, plane, K-half) is ONE 4-D
+//             TMA box (64 ch x 8 x 8 x 1) landing directly in the 128B-swizzled K-major operand layout; 2 stages
+//   B tile  [ 64 x 128] : the 49 support vectors of (n,l), split-bf16, built once per unit by 2 warps
+//   D       [128 x  64] : fp32 in TMEM, 3 tcgen05.mma per k16 step (lo*hi + hi*lo + hi*hi), 2 accumulators
+//   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
+//             row -> shared [row][a][k] -> y-blend + split-bf16 -> 128-byte coalesced stores of the volume rows
+//             (K padding written as zeros)
+// Warps: 0 TMA issuer, 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace ct3 {
+namespace {
+
+constexpr int TMA_WARP = 0;
+constexpr int MMA_WARP = 1;
+constexpr int SB_WARP0 = 2;               // 2 support-builder warps
+constexpr int EPI_WARP0 = 4;              // warps 4..7 group 0, 8..11 group 1; (warp & 3) = TMEM lane quarter
+constexpr int THREADS = 12 * 32;
+constexpr int A_PLANE = 2 * 16384;        // one bf16 plane of A: 2 K-halves x [128 rows x 128 B]
+constexpr int A_STAGE = 2 * A_PLANE;      // hi + lo = 64 KiB
+constexpr int S_PART = 2 * 8192;          // one plane of S: 2 K-halves x [64 rows x 128 B]
+constexpr int S_BYTES = 2 * S_PART;       // 32 KiB
+constexpr int H_FRAME = 8 * 7 * kP;       // floats: x-blended correlations [row 8][a 7][k 49] of one frame
+constexpr int H_GROUP = 2 * H_FRAME * 4;  // bytes per epilogue group (2 frames)
+constexpr int PAIRS = kVolPad / 2;        // 4-byte bf16 pairs per plane of one volume row
+constexpr int OFF_A = 0;
+constexpr int OFF_S = OFF_A + 2 * A_STAGE;
+constexpr int OFF_H = OFF_S + S_BYTES;
+constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*343, row1*343, -}
+constexpr int OFF_PARAM = OFF_TAB + 2 * 2 * 8 * 16;  // [slot 4][frame 2] x {cx, cy, box_x, box_y}
+constexpr int OFF_BAR = OFF_PARAM + 4 * 2 * 16;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr uint32_t TMEM_COLS = 128;       // 2 accumulators x 64 columns
+
+struct Corr2Args {
+  PyramidLayout lay;
+  const float* support;        // [4][49, N, 128]
+  const uint8_t* track_valid;  // [N] or null
+  const float* coords;         // [T, N, 2]
+  int T, N;
+  __nv_bfloat16* vol;          // [N*T*4, 2*kVolPad]
+};
+struct Corr2Maps {
+  CUtensorMap m[kL];           // per level: bf16 dims (128, W, H, 2T), box (64, 8, 8, 1), 128B swizzle
+};
+
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// origin of the 8-wide box holding every tap of the 7 border-clamped samples around c (size >= 8)
+__device__ __forceinline__ int box_origin8(float c, int size) {
+  const float cc = fminf(fmaxf(c, -16.f), (float)size + 16.f);
+  return max(0, min((int)floorf(cc) - kR, size - 8));
+}
+
+// one border-clamped sample coordinate -> (tap0, tap1) relative to the box origin and the weight of tap1.
+// A zero weight folds tap1 onto tap0, which also absorbs the fp32 case c + offset rounding up to an integer.
+__device__ __forceinline__ void tap_pair(float c, int off, int size, int origin, int& s0, int& s1, float& w) {
+  const float x = fminf(fmaxf(c + (float)off, 0.f), (float)(size - 1));
+  const float xf = floorf(x);
+  const int x0 = (int)xf;
+  w = x - xf;
+  s0 = min(max(x0 - origin, 0), 7);
+  s1 = (w > 0.f) ? min(max(min(x0 + 1, size - 1) - origin, 0), 7) : s0;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant__ Corr2Maps maps, int num_units) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* a_full = bars;          // [2] TMA -> MMA             (count 1 + tx bytes)
+  uint64_t* a_empty = bars + 2;     // [2] MMA -> TMA             (tcgen05.commit)
+  uint64_t* d_full = bars + 4;      // [2] MMA -> epilogue group  (tcgen05.commit)
+  uint64_t* d_empty = bars + 6;     // [2] epilogue group -> MMA  (count 4)
+  uint64_t* s_full = bars + 8;      // builders -> MMA, per unit  (count 2)
+  uint64_t* s_empty = bars + 9;     // MMA -> builders, per unit  (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_unit = (g.T + 1) / 2;
+
+  // one-time: zero S (rows 49..63 stay zero forever)
+  for (int i = threadIdx.x; i < S_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_S)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 4);
+    }
+    mbar_init(s_full, 2);
+    mbar_init(s_empty, 1);
+    fence_barrier_init();
+    for (int l = 0; l < kL; ++l) tma_prefetch_desc(&maps.m[l]);
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TMA_WARP) {
+    // ================================================================== TMA issuer (whole warp walks, lane 0 issues)
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int n = u / kL, l = u % kL;
+      const int H = g.lay.h[l], W = g.lay.w[l];
+      const float inv = 1.0f / (float)(1 << l);
+      for (int t0 = 0; t0 < g.T; t0 += 32) {
+        // coordinates of up to 32 frames in one round trip (lane = frame), then broadcast per tile
+        const int tl = min(t0 + lane, g.T - 1);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(g.coords + ((int64_t)tl * g.N + n) * 2));
+        const int cnt = min(32, g.T - t0);
+        for (int k = 0; k < cnt; k += 2, ++it) {
+          const int k1 = min(k + 1, 31);
+          const float cx0 = __shfl_sync(0xffffffffu, c.x, k) * inv, cy0 = __shfl_sync(0xffffffffu, c.y, k) * inv;
+          const float cx1 = __shfl_sync(0xffffffffu, c.x, k1) * inv, cy1 = __shfl_sync(0xffffffffu, c.y, k1) * inv;
+          if (lane == 0) {
+            const int nf = (k + 1 < cnt) ? 2 : 1;
+            const int st = it & 1;
+            mbar_wait(&a_empty[st], ((it >> 1) & 1u) ^ 1u);
+            const int bx0 = box_origin8(cx0, W), by0 = box_origin8(cy0, H);
+            const int bx1 = box_origin8(cx1, W), by1 = box_origin8(cy1, H);
+            float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it & 3) * 32);
+            prm[0] = make_float4(cx0, cy0, __int_as_float(bx0), __int_as_float(by0));
+            prm[1] = make_float4(cx1, cy1, __int_as_float(bx1), __int_as_float(by1));
+            mbar_arrive_expect_tx(&a_full[st], (uint32_t)(nf * (A_STAGE / 2)));
+            uint8_t* dst = smem + OFF_A + st * A_STAGE;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              if (f < nf) {
+                const int bx = f ? bx1 : bx0, by = f ? by1 : by0;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                  for (int kh = 0; kh < 2; ++kh)
+                    tma_load_4d(dst + pl * A_PLANE + kh * 16384 + f * 8192, &maps.m[l], kh * 64, bx, by,
+                                pl * g.T + t0 + k + f, &a_full[st]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      uint32_t it = 0, ui = 0;
+      const uint32_t s_base = smem_u32(smem + OFF_S);
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+        mbar_wait(s_full, ui & 1u);
+        for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
+          const int st = it & 1;
+          mbar_wait(&a_full[st], (it >> 1) & 1u);
+          mbar_wait(&d_empty[st], ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(st * 64);
+          const uint32_t a_base = smem_u32(smem + OFF_A + st * A_STAGE);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t ao = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
+            const uint32_t so = (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32);
+            const uint64_t dah = umma_desc_sw128(a_base + ao), dal = umma_desc_sw128(a_base + A_PLANE + ao);
+            const uint64_t dsh = umma_desc_sw128(s_base + so), dsl = umma_desc_sw128(s_base + S_PART + so);
+            umma_bf16(d_tmem, dal, dsh, idesc, ks != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, dah, dsl, idesc, 1u);
+            umma_bf16(d_tmem, dah, dsh, idesc, 1u);
+          }
+          umma_commit(&a_empty[st]);
+          umma_commit(&d_full[st]);
+        }
+        umma_commit(s_empty);
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    // ================================================================== support builders (B operand, once per unit)
+    const int sb = warp - SB_WARP0;
+    const int atom = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;  // where this lane's 4 channels live
+    uint8_t* s_hi = smem + OFF_S;
+    uint32_t ui = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+      const int n = u / kL, l = u % kL;
+      const bool valid = g.track_valid == nullptr || g.track_valid[n] != 0;
+      float4 rows[25];
+#pragma unroll
+      for (int j = 0; j < 25; ++j) {
+        const int p = sb + 2 * j;
+        rows[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < kP && valid)
+          rows[j] = __ldg(reinterpret_cast<const float4*>(g.support + ((int64_t)l * kP * g.N + (int64_t)p * g.N + n) * kD) + lane);
+      }
+      if (ui > 0) mbar_wait(s_empty, (ui - 1) & 1u);   // MMAs of the previous unit have retired
+#pragma unroll
+      for (int j = 0; j < 25; ++j) {
+        const int p = sb + 2 * j;
+        if (p < kP) {
+          uint32_t h0, l0, h1, l1;
+          split2(rows[j].x, rows[j].y, h0, l0);
+          split2(rows[j].z, rows[j].w, h1, l1);
+          const uint32_t off = (uint32_t)(atom * 8192) + sw128(p, chunk) + (uint32_t)(half * 8);
+          *reinterpret_cast<uint2*>(s_hi + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(s_hi + S_PART + off) = make_uint2(l0, l1);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full);
+    }
+  } else {
+    // ================================================================== epilogue
+    const int grp = (warp - EPI_WARP0) >> 2;   // tiles with (it & 1) == grp, accumulator grp
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int r = q * 32 + lane;               // D row = f*64 + y*8 + x
+    const int f = r >> 6, py = (r >> 3) & 7, px = r & 7;
+    const int a = min(px, 6);                  // x-offset index this lane blends (lane px == 7 only feeds others)
+    float* hbuf = reinterpret_cast<float*>(smem + OFF_H + grp * H_GROUP);
+    float4* tab = reinterpret_cast<float4*>(smem + OFF_TAB + grp * 256);
+    float* hrow = hbuf + f * H_FRAME + (py * 7 + a) * kP;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 64);
+    const int bar_id = 1 + grp;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int n = u / kL, l = u % kL;
+      const int H = g.lay.h[l], W = g.lay.w[l];
+      for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
+        if ((int)(it & 1u) != grp) continue;
+        mbar_wait(&d_full[grp], (it >> 1) & 1u);
+        tc_fence_after_sync();
+        const float4 prm = *reinterpret_cast<const float4*>(smem + OFF_PARAM + (it & 3) * 32 + f * 16);
+        const int bx = __float_as_int(prm.z), by = __float_as_int(prm.w);
+        int sx0, sx1;
+        float wx;
+        tap_pair(prm.x, a - kR, W, bx, sx0, sx1, wx);
+        const float ux = 1.f - wx;
+        const int src0 = (lane & 24) | sx0, src1 = (lane & 24) | sx1;
+        // ---- x-blend: h[row][a][k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k]
+        float v[32];
+        tmem_ld32(taddr, v);                       // columns 0..31
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float v0 = __shfl_sync(0xffffffffu, v[k], src0), v1 = __shfl_sync(0xffffffffu, v[k], src1);
+          if (px < 7) hrow[k] = ux * v0 + wx * v1;
+        }
+        tmem_ld32(taddr + 32, v);                  // columns 32..63 (32..48 used)
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
+#pragma unroll
+        for (int k = 0; k < kP - 32; ++k) {
+          const float v0 = __shfl_sync(0xffffffffu, v[k], src0), v1 = __shfl_sync(0xffffffffu, v[k], src1);
+          if (px < 7) hrow[32 + k] = ux * v0 + wx * v1;
+        }
+        if ((r & 63) < 7) {                         // y taps of sample row b, shared by the whole frame
+          int r0, r1;
+          float wy;
+          tap_pair(prm.y, (r & 63) - kR, H, by, r0, r1, wy);
+          tab[f * 8 + (r & 63)] = make_float4(wy, __int_as_float(r0 * 7 * kP), __int_as_float(r1 * 7 * kP), 0.f);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // ---- y-blend + split + store: element o = (a*7+b)*49 + k of each frame, 2 elements per thread and step
+        for (int p = r; p < 2 * PAIRS; p += 128) {
+          const int ff = p >= PAIRS ? 1 : 0;
+          const int pp = p - ff * PAIRS;
+          const int t = 2 * tp + ff;
+          if (t >= g.T) continue;
+          const int o = 2 * pp;
+          float e[2] = {0.f, 0.f};
+          int rho = (o * 1338) >> 16;               // o / 49 for o < 2432
+          int k = o - rho * kP;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (o + j < kVol) {
+              const int aa = (rho * 37) >> 8;       // rho / 7 for rho < 49
+              const int bb = rho - aa * 7;
+              const float4 tb = tab[ff * 8 + bb];
+              const float* hb = hbuf + ff * H_FRAME + aa * kP + k;
+              e[j] = (1.f - tb.x) * hb[__float_as_int(tb.y)] + tb.x * hb[__float_as_int(tb.z)];
+            }
+            if (++k == kP) { k = 0; ++rho; }
+          }
+          uint32_t hi, lo;
+          split2(e[0], e[1], hi, lo);
+          uint32_t* grow = reinterpret_cast<uint32_t*>(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad));
+          grow[pp] = hi;
+          grow[PAIRS + pp] = lo;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // h / tab may be overwritten by the next tile
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// fp32 channels-last level -> [hi plane | lo plane] bf16, 4 channels per thread
+__global__ void __launch_bounds__(256)
+split_level_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    uint32_t h0, l0, h1, l1;
+    split2(v.x, v.y, h0, l0);
+    split2(v.z, v.w, h1, l1);
+    hi[i] = make_uint2(h0, h1);
+    lo[i] = make_uint2(l0, l1);
+  }
+}
+
+}  // namespace
+
+bool corr_patch_supported(int T, int H4, int W4) {
+  const PyramidLayout lay = pyramid_layout(T, H4, W4);
+  return lay.h[kL - 1] >= 8 && lay.w[kL - 1] >= 8;
+}
+
+cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_bfloat16* pyr_split, cudaStream_t s) {
+  const PyramidLayout lay = pyramid_layout(T, H4, W4);
+  for (int l = 0; l < kL; ++l) {
+    const int64_t n = (int64_t)T * lay.h[l] * lay.w[l] * kD;
+    __nv_bfloat16* dst = pyr_split + 2 * lay.off[l];
+    const int64_t n4 = n / 4;
+    const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    split_level_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(pyr + lay.off[l]),
+                                            reinterpret_cast<uint2*>(dst), reinterpret_cast<uint2*>(dst + n), n4);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
+                                 const uint8_t* track_valid, const float* coords, int T, int N,
+                                 __nv_bfloat16* vol_split, int num_sms, cudaStream_t s) {
+  Corr2Args g;
+  g.lay = pyramid_layout(T, H4, W4);
+  g.support = support;
+  g.track_valid = track_valid;
+  g.coords = coords;
+  g.T = T;
+  g.N = N;
+  g.vol = vol_split;
+  Corr2Maps maps;
+  for (int l = 0; l < kL; ++l) {
+    const uint64_t W = (uint64_t)g.lay.w[l], H = (uint64_t)g.lay.h[l];
+    if (W < 8 || H < 8) return cudaErrorInvalidValue;
+    const uint64_t dims[4] = {(uint64_t)kD, W, H, (uint64_t)(2 * T)};   // dim 3 = plane*T + t
+    const uint64_t strides[3] = {(uint64_t)kD * 2, W * kD * 2, H * W * kD * 2};
+    const uint32_t box[4] = {64, 8, 8, 1};
+    if (!encode_tensor_map(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pyr_split + 2 * g.lay.off[l], dims, strides,
+                           box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return cudaErrorInvalidValue;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(corr_patch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int num_units = N * kL;
+  const int grid = num_units < num_sms ? num_units : num_sms;
+  corr_patch_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
+  return cudaGetLastError();
+}
+
+}  // namespace ct3

@@ -31,13 +31,23 @@ cudaError_t launch_upsample_concat(const float* const src[4], const int c[4], co
 
 // ---- corr.cu : correlation sampling ---------------------------------------------------------------
 // vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level
-cudaError_t launch_corr_sample(const float* pyr, int H4, int W4, const float* support,
+// impl: 0 tensor cores (corr_tc2.cu when pyr_split is given and every level is >= 8x8, else corr_tc.cu),
+//       1 exact-fp32 SIMT, 2 corr_tc.cu always
+cudaError_t launch_corr_sample(const float* pyr, const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                const uint8_t* track_valid, const float* coords, int T, int N,
                                __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s);
 
 cudaError_t launch_corr_sample_tc(const float* pyr, int H4, int W4, const float* support,
                                   const uint8_t* track_valid, const float* coords, int T, int N,
                                   __nv_bfloat16* vol_split, int num_sms, cudaStream_t s);
+
+// corr_tc2.cu: correlate-then-interpolate on a split-bf16 copy of the pyramid
+//   pyr_split: per level at bf16 offset 2*off[l]: [plane hi|lo][T][H][W][128]   (same bytes as the fp32 pyramid)
+bool corr_patch_supported(int T, int H4, int W4);
+cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_bfloat16* pyr_split, cudaStream_t s);
+cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
+                                 const uint8_t* track_valid, const float* coords, int T, int N,
+                                 __nv_bfloat16* vol_split, int num_sms, cudaStream_t s);
 
 // ---- tokens.cu : elementwise / row-wise pieces of the transformer ---------------------------------
 cudaError_t launch_layernorm_split(const float* x, int rows, const float* gamma, const float* beta, float eps,

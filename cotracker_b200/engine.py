@@ -41,10 +41,11 @@ def _declare(lib):
         "ct3_pyramid_layout": (c_int, [c_int, c_int, c_int, i64p, intp, intp, i64p]),
         "ct3_prepare_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_sample_support": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
-        "ct3_workspace_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
+        "ct3_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
         "ct3_update_loop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-        "ct3_corr_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_corr_sample": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
         "ct3_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_split_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_updateformer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -195,9 +196,10 @@ def sample_support(pyr, T, H4, W4, qframes, qcoords, support=None, accumulate_ma
     return support
 
 
-def workspace_bytes(T: int, N: int) -> int:
+def workspace_bytes(T: int, N: int, H4: int = 0, W4: int = 0) -> int:
+    """Scratch of ct3_update_loop for T frames of H4 x W4 feature maps and N tracks (H4 = W4 = 0: updateformer only)."""
     n = ctypes.c_size_t(0)
-    _check(lib().ct3_workspace_bytes(T, N, ctypes.byref(n)), "ct3_workspace_bytes")
+    _check(lib().ct3_workspace_bytes(T, N, H4, W4, ctypes.byref(n)), "ct3_workspace_bytes")
     return n.value
 
 
@@ -207,8 +209,8 @@ class WorkspaceCache:
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
 
-    def get(self, T: int, N: int, device) -> torch.Tensor:
-        need = workspace_bytes(T, N)
+    def get(self, T: int, N: int, device, H4: int = 0, W4: int = 0) -> torch.Tensor:
+        need = workspace_bytes(T, N, H4, W4)
         if self.buf is None or self.buf.numel() < need or self.buf.device != torch.device(device):
             self.buf = None
             self.buf = torch.empty(need, dtype=torch.uint8, device=device)
@@ -231,13 +233,16 @@ def update_loop(packed, pyr, H4, W4, support, track_valid, coords, vis, conf, ti
 
 
 # ---- stage-level wrappers (tests, profiles) -----------------------------------------------------------
-def corr_sample(pyr, H4, W4, support, track_valid, coords) -> torch.Tensor:
-    """-> fp32 correlation volume [N, T, 4, 2401] reconstructed from the split-bf16 device layout."""
+def corr_sample(pyr, H4, W4, support, track_valid, coords, scratch: bool = True) -> torch.Tensor:
+    """-> fp32 correlation volume [N, T, 4, 2401] reconstructed from the split-bf16 device layout.
+    scratch=False withholds the split-pyramid scratch, i.e. selects the sample-then-correlate kernel."""
     T, N, _ = coords.shape
     vol = torch.empty(N * T * LEVELS, 2 * VOL_PAD, dtype=torch.bfloat16, device=coords.device)
+    scr = torch.empty(pyr.numel() * 4, dtype=torch.uint8, device=coords.device) if scratch else None
     with torch.cuda.device(coords.device):
         _check(lib().ct3_corr_sample(_ptr(pyr), H4, W4, _ptr(support), _ptr(track_valid), _ptr(coords), T, N, _ptr(vol),
-                                     _stream(coords.device)), "ct3_corr_sample")
+                                     _ptr(scr), scr.numel() if scratch else 0, _stream(coords.device)),
+               "ct3_corr_sample")
     v = vol.float()
     full = v[:, :VOL_PAD] + v[:, VOL_PAD:]
     assert bool((full[:, VOL:] == 0).all()), "K padding of the correlation volume must be zero"

@@ -188,7 +188,7 @@ class CoTrackerThreeBase(nn.Module):
         T, N, _ = coords.shape
         dev = coords.device
         engine.update_loop(self.packed_weights(dev), pyr, H4, W4, support, track_valid, coords, vis, conf,
-                           self.interpolate_time_embed(T).to(dev), iters, self._ws.get(T, N, dev))
+                           self.interpolate_time_embed(T).to(dev), iters, self._ws.get(T, N, dev, H4, W4))
 
 
 class CoTrackerThreeOffline(CoTrackerThreeBase):

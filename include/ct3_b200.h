@@ -70,8 +70,9 @@ const char* ct3_weight_name(int index);           /* state-dict key of tensor #i
 int ct3_version(void);
 const char* ct3_last_error(void);
 
-/* Debug/verification options ("gemm": 0 = tcgen05 tensor-core path (default),
- * 1 = SIMT fp32 verification kernel used by the tests to cross-check). */
+/* Debug/verification options ("gemm", "corr", "attn": 0 = tensor-core path (default),
+ * 1 = SIMT fp32 verification kernel used by the tests to cross-check; "corr" = 2 forces the
+ * sample-then-correlate tensor-core kernel that otherwise only serves pyramids with a level below 8x8). */
 int ct3_set_option(const char* name, int value);
 int ct3_get_option(const char* name, int* value);
 
@@ -122,8 +123,10 @@ int ct3_enc_tail(const void* packed, const float* cat, int T, int H4, int W4, fl
                  size_t workspace_bytes, ct3_stream_t stream);
 
 /* ---- the hot loop -----------------------------------------------------------
- * ct3_workspace_bytes: scratch needed by ct3_update_loop / ct3_update_iter. */
-int ct3_workspace_bytes(int T, int N, size_t* out_bytes);
+ * ct3_workspace_bytes: scratch needed by ct3_update_loop for a window of T frames of H4 x W4 feature maps and N
+ * tracks (includes the split-bf16 copy of the pyramid the correlation kernel reads through TMA);
+ * H4 = W4 = 0 sizes it for ct3_updateformer alone. */
+int ct3_workspace_bytes(int T, int N, int H4, int W4, size_t* out_bytes);
 
 /* ct3_update_loop: `iters` refinement iterations, in place on the state.
  *   packed   : ct3_pack_weights output
@@ -153,9 +156,12 @@ int ct3_profile_read(double ms[5], int launches[5], double* gemm_flops);
  * cotracker3_online.py:130-143, cotracker3_offline.py:144-156) for all levels:
  * vol_split [N*T*4, 2*2432] bf16: row ((n*T+t)*4+level), hi plane cols [0,2432),
  * lo plane cols [2432,4864); value = hi+lo, cols 2401..2431 are zero. */
+/* scratch: ct3_pyramid_layout's total * 4 bytes (256-byte aligned) for the split-bf16 pyramid copy of the
+ * correlate-then-interpolate kernel (used when every level is >= 8x8 texels); NULL selects the
+ * sample-then-correlate kernel. */
 int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support,
                     const uint8_t* track_valid, const float* coords, int T, int N,
-                    void* vol_split, ct3_stream_t stream);
+                    void* vol_split, void* scratch, size_t scratch_bytes, ct3_stream_t stream);
 
 /* Generic split-bf16x3 linear layer  Y = act(X W^T + b)  (nn.Linear, blocks.py:61-67)
  *   x_split [M, 2*Kpad] bf16 (hi|lo), w_split [Nout, 2*Kpad] bf16, bias [Nout] fp32 or NULL

@@ -7,6 +7,7 @@ from cotracker_b200.predictor import CoTrackerPredictor, get_points_on_a_grid
 from cotracker_b200.synthetic import seeded_state_dict, texture_video
 
 dev = "cuda:0"
+engine.set_option("corr", int(os.environ.get("CT3_CORR", "0")))   # 0 product, 1 SIMT, 2 sample-then-correlate
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 grids = [int(g) for g in sys.argv[1].split(",")] if len(sys.argv) > 1 else [10, 20, 40, 80]
 p = CoTrackerPredictor(checkpoint=None, window_len=60)
@@ -28,7 +29,7 @@ for G in grids:
     qc = (pts / 4).contiguous()
     sup, ms = sync_time(lambda: engine.sample_support(pyr, T, 96, 128, qf, qc)); print(f"G={G} support {ms:.2f} ms", flush=True)
     coords = qc[None].expand(T, N, 2).contiguous(); vis = torch.zeros(T, N, device=dev); conf = torch.zeros(T, N, device=dev)
-    ws = torch.empty(engine.workspace_bytes(T, N), dtype=torch.uint8, device=dev)
+    ws = torch.empty(engine.workspace_bytes(T, N, 96, 128), dtype=torch.uint8, device=dev)
     packed = m.packed_weights(torch.device(dev)); te = m.interpolate_time_embed(T).to(dev)
     for rep in range(2):
         engine.profile_enable(True)

@@ -68,7 +68,7 @@ def test_loop_tensor_core_vs_simt_full_size(T):
     support = eng.sample_support(pyr, T, H4, W4, qf, qc)
     packed = eng.pack_weights(sd, DEV)
     te = O.time_embedding(sd, T)[0].contiguous().to(DEV)
-    ws = torch.empty(eng.workspace_bytes(T, N), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(eng.workspace_bytes(T, N, H4, W4), dtype=torch.uint8, device=DEV)
     out = {}
     for mode in (0, 1):
         coords = qc[None].expand(T, N, 2).contiguous().clone()

@@ -106,8 +106,12 @@ def test_sample_support(eng):
     assert bool((acc[:, :, ~sel] == 1).all())
 
 
-@pytest.mark.parametrize("impl", [0, 1])   # 0: tcgen05 fused kernel (product), 1: exact-fp32 SIMT cross-check
-@pytest.mark.parametrize("T,N,H4,W4", [(3, 16, 24, 32), (2, 9, 8, 8), (5, 33, 96, 128), (1, 5, 16, 24), (16, 300, 96, 128)])
+# impl 0: tensor-core product path (correlate-then-interpolate kernel when every level is >= 8x8, i.e. the
+# 64x64 / 64x72 / 96x128 cases; sample-then-correlate otherwise), 1: exact-fp32 SIMT cross-check,
+# 2: sample-then-correlate tensor-core kernel forced
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("T,N,H4,W4", [(3, 16, 24, 32), (2, 9, 8, 8), (5, 33, 96, 128), (1, 5, 16, 24), (16, 300, 96, 128),
+                                       (2, 40, 64, 64), (3, 150, 64, 72)])
 def test_corr_sample(eng, impl, T, N, H4, W4):
     fmaps = _pyramid_case(T, H4, W4, seed=2)
     want_pyr = O.normalized_pyramid(fmaps)
@@ -192,10 +196,11 @@ def test_corr_mlp_gelu_variant_is_erf(eng):
 
 
 @pytest.mark.parametrize("impl", [0, 1])
-def test_update_loop_vs_oracle(eng, impl):
+@pytest.mark.parametrize("H4,W4", [(24, 32), (64, 72)])   # 64x72: every level >= 8x8 -> correlate-then-interpolate kernel
+def test_update_loop_vs_oracle(eng, impl, H4, W4):
     """The hot loop alone: identical pyramid/support on both sides, amplified heads (several px of motion)."""
     sd = _amplified_sd(seed=7, head_gain=10.0, vis_gain=100.0)
-    T, N, H4, W4, iters = 7, 37, 24, 32, 4
+    T, N, iters = 7, 37, 4
     fmaps = _pyramid_case(T, H4, W4, seed=4)
     pyr_cpu = O.normalized_pyramid(fmaps)
     g = torch.Generator().manual_seed(31)
@@ -209,7 +214,7 @@ def test_update_loop_vs_oracle(eng, impl):
     support = torch.stack(sup_cpu).to(DEV).contiguous()
     packed = eng.pack_weights(sd, DEV)
     coords, vis, conf = c0.to(DEV).clone(), torch.zeros(T, N, device=DEV), torch.zeros(T, N, device=DEV)
-    ws = torch.empty(eng.workspace_bytes(T, N), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(eng.workspace_bytes(T, N, H4, W4), dtype=torch.uint8, device=DEV)
     te = O.time_embedding(sd, T)[0].contiguous().to(DEV)
     eng.set_option("gemm", impl)
     try:
@@ -237,7 +242,7 @@ def test_update_loop_cluster_gemm_vs_simt_at_scale(eng):
     support = eng.sample_support(pyr, T, H4, W4, qf, qc)
     packed = eng.pack_weights(sd, DEV)
     te = O.time_embedding(sd, T)[0].contiguous().to(DEV)
-    ws = torch.empty(eng.workspace_bytes(T, N), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(eng.workspace_bytes(T, N, H4, W4), dtype=torch.uint8, device=DEV)
     out = {}
     for impl in (0, 1):
         coords = qc[None].expand(T, N, 2).contiguous().clone()

@@ -27,10 +27,10 @@ def test_abi_argument_validation_without_gpu():
     from cotracker_b200 import engine
     lib = engine.lib()
     n = ctypes.c_size_t(0)
-    assert lib.ct3_workspace_bytes(16, 6400, ctypes.byref(n)) == 0 and n.value > 6e9
-    assert lib.ct3_workspace_bytes(0, 10, ctypes.byref(n)) == -1          # CT3_EINVAL
+    assert lib.ct3_workspace_bytes(16, 6400, 96, 128, ctypes.byref(n)) == 0 and n.value > 6e9
+    assert lib.ct3_workspace_bytes(0, 10, 0, 0, ctypes.byref(n)) == -1          # CT3_EINVAL
     assert b"T and N" in lib.ct3_last_error()
-    assert lib.ct3_workspace_bytes(4, 4, None) == -1
+    assert lib.ct3_workspace_bytes(4, 4, 0, 0, None) == -1
     off, h, w, total = engine.pyramid_layout(16, 96, 128)
     assert h == [96, 48, 24, 12] and w == [128, 64, 32, 16] and total == 16 * 16320 * 128
     with pytest.raises(engine.EngineError):
