@@ -17,8 +17,9 @@
 //   B tile  [ 64 x 128] : the 49 support vectors of (n,l), split-bf16, built once per unit by 2 warps
 //   D       [128 x  64] : fp32 in TMEM, 3 tcgen05.mma per k16 step (lo*hi + hi*lo + hi*hi), 2 accumulators
 //   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
-//             row -> shared [row][a][k] -> y-blend + split-bf16 -> 128-byte coalesced stores of the volume rows
-//             (K padding written as zeros)
+//             row -> shared [row][a][k] (16-byte vectors) -> y-blend in registers, one thread per volume row ->
+//             split-bf16 byte image of the two 9728-byte volume rows (reusing the blend buffer, K padding zero)
+//             -> fully coalesced 16-byte stores
 // Warps: 0 TMA issuer, 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -35,13 +36,16 @@ constexpr int A_PLANE = 2 * 16384;        // one bf16 plane of A: 2 K-halves x [
 constexpr int A_STAGE = 2 * A_PLANE;      // hi + lo = 64 KiB
 constexpr int S_PART = 2 * 8192;          // one plane of S: 2 K-halves x [64 rows x 128 B]
 constexpr int S_BYTES = 2 * S_PART;       // 32 KiB
-constexpr int H_FRAME = 8 * 7 * kP;       // floats: x-blended correlations [row 8][a 7][k 49] of one frame
+constexpr int H_A = 52;                   // floats per (texel row, a): 49 + pad, keeps every vector 16-byte aligned
+constexpr int H_ROW = 7 * H_A;            // floats per texel row
+constexpr int H_FRAME = 8 * H_ROW;        // floats: x-blended correlations [row 8][a 7][k 52] of one frame
 constexpr int H_GROUP = 2 * H_FRAME * 4;  // bytes per epilogue group (2 frames)
-constexpr int PAIRS = kVolPad / 2;        // 4-byte bf16 pairs per plane of one volume row
+constexpr int ROW_BYTES = 2 * kVolPad * 2;   // 9728: one volume row image [hi | lo]
+static_assert(2 * ROW_BYTES <= H_GROUP, "the output image of a tile reuses the blend buffer");
 constexpr int OFF_A = 0;
 constexpr int OFF_S = OFF_A + 2 * A_STAGE;
 constexpr int OFF_H = OFF_S + S_BYTES;
-constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*343, row1*343, -}
+constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*H_ROW, row1*H_ROW, -}
 constexpr int OFF_PARAM = OFF_TAB + 2 * 2 * 8 * 16;  // [slot 4][frame 2] x {cx, cy, box_x, box_y}
 constexpr int OFF_BAR = OFF_PARAM + 4 * 2 * 16;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -229,14 +233,21 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
     // ================================================================== epilogue
     const int grp = (warp - EPI_WARP0) >> 2;   // tiles with (it & 1) == grp, accumulator grp
     const int q = warp & 3;                    // TMEM lane quarter
-    const int r = q * 32 + lane;               // D row = f*64 + y*8 + x
+    const int r = q * 32 + lane;               // D row = f*64 + y*8 + x; also this thread's index in the group
     const int f = r >> 6, py = (r >> 3) & 7, px = r & 7;
     const int a = min(px, 6);                  // x-offset index this lane blends (lane px == 7 only feeds others)
     float* hbuf = reinterpret_cast<float*>(smem + OFF_H + grp * H_GROUP);
+    uint8_t* img = smem + OFF_H + grp * H_GROUP;     // output image of the tile, reuses hbuf once it has been read
     float4* tab = reinterpret_cast<float4*>(smem + OFF_TAB + grp * 256);
-    float* hrow = hbuf + f * H_FRAME + (py * 7 + a) * kP;
+    float4* hrow = reinterpret_cast<float4*>(hbuf + f * H_FRAME + py * H_ROW + a * H_A);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 64);
     const int bar_id = 1 + grp;
+    // y-blend role: thread r < 98 owns volume row (frame yf, sample rho = ya*7 + yb) of the tile
+    const bool yrow = r < 2 * kP;
+    const int yf = r >= kP ? 1 : 0;
+    const int rho = r - yf * kP;
+    const int ya = rho / 7, yb = rho - ya * 7;
+    const bool odd = (rho & 1) != 0;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int n = u / kL, l = u % kL;
@@ -252,58 +263,97 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         tap_pair(prm.x, a - kR, W, bx, sx0, sx1, wx);
         const float ux = 1.f - wx;
         const int src0 = (lane & 24) | sx0, src1 = (lane & 24) | sx1;
-        // ---- x-blend: h[row][a][k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k]
+        // ---- x-blend: h[row][a][k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k], 4 k per shared-memory store
         float v[32];
         tmem_ld32(taddr, v);                       // columns 0..31
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v0 = __shfl_sync(0xffffffffu, v[k], src0), v1 = __shfl_sync(0xffffffffu, v[k], src1);
-          if (px < 7) hrow[k] = ux * v0 + wx * v1;
+        for (int k4 = 0; k4 < 8; ++k4) {
+          float hv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v0 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src0), v1 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src1);
+            hv[j] = ux * v0 + wx * v1;
+          }
+          if (px < 7) hrow[k4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
         tmem_ld32(taddr + 32, v);                  // columns 32..63 (32..48 used)
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
 #pragma unroll
-        for (int k = 0; k < kP - 32; ++k) {
-          const float v0 = __shfl_sync(0xffffffffu, v[k], src0), v1 = __shfl_sync(0xffffffffu, v[k], src1);
-          if (px < 7) hrow[32 + k] = ux * v0 + wx * v1;
+        for (int k4 = 0; k4 < 5; ++k4) {
+          float hv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * k4 + j < kP - 32) {
+              const float v0 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src0), v1 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src1);
+              hv[j] = ux * v0 + wx * v1;
+            }
+          }
+          if (px < 7) hrow[8 + k4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
         if ((r & 63) < 7) {                         // y taps of sample row b, shared by the whole frame
           int r0, r1;
           float wy;
           tap_pair(prm.y, (r & 63) - kR, H, by, r0, r1, wy);
-          tab[f * 8 + (r & 63)] = make_float4(wy, __int_as_float(r0 * 7 * kP), __int_as_float(r1 * 7 * kP), 0.f);
+          tab[f * 8 + (r & 63)] = make_float4(wy, __int_as_float(r0 * H_ROW), __int_as_float(r1 * H_ROW), 0.f);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        // ---- y-blend + split + store: element o = (a*7+b)*49 + k of each frame, 2 elements per thread and step
-        for (int p = r; p < 2 * PAIRS; p += 128) {
-          const int ff = p >= PAIRS ? 1 : 0;
-          const int pp = p - ff * PAIRS;
-          const int t = 2 * tp + ff;
-          if (t >= g.T) continue;
-          const int o = 2 * pp;
-          float e[2] = {0.f, 0.f};
-          int rho = (o * 1338) >> 16;               // o / 49 for o < 2432
-          int k = o - rho * kP;
+        // ---- y-blend in registers: e[k] = (1-wy) h[row0][a][k] + wy h[row1][a][k] for this thread's volume row
+        float e[H_A];
+        if (yrow) {
+          const float4 tb = tab[yf * 8 + yb];
+          const float4* h0 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.y));
+          const float4* h1 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.z));
+          const float wy = tb.x, uy = 1.f - tb.x;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (o + j < kVol) {
-              const int aa = (rho * 37) >> 8;       // rho / 7 for rho < 49
-              const int bb = rho - aa * 7;
-              const float4 tb = tab[ff * 8 + bb];
-              const float* hb = hbuf + ff * H_FRAME + aa * kP + k;
-              e[j] = (1.f - tb.x) * hb[__float_as_int(tb.y)] + tb.x * hb[__float_as_int(tb.z)];
-            }
-            if (++k == kP) { k = 0; ++rho; }
+          for (int k4 = 0; k4 < H_A / 4; ++k4) {
+            const float4 p0 = h0[k4], p1 = h1[k4];
+            e[4 * k4 + 0] = uy * p0.x + wy * p1.x;
+            e[4 * k4 + 1] = uy * p0.y + wy * p1.y;
+            e[4 * k4 + 2] = uy * p0.z + wy * p1.z;
+            e[4 * k4 + 3] = uy * p0.w + wy * p1.w;
           }
-          uint32_t hi, lo;
-          split2(e[0], e[1], hi, lo);
-          uint32_t* grow = reinterpret_cast<uint32_t*>(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad));
-          grow[pp] = hi;
-          grow[PAIRS + pp] = lo;
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // h / tab may be overwritten by the next tile
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // h fully read: the image may overwrite it
+        // ---- split-bf16 byte image of the tile's two volume rows ([hi(2432) | lo(2432)] each)
+        if (yrow) {
+          // 49 bf16 per plane at element offset rho*49: one 2-byte edge element (the first if that offset is odd,
+          // else the last) + 24 aligned 4-byte pairs
+          __nv_bfloat16* dst_hi = reinterpret_cast<__nv_bfloat16*>(img + yf * ROW_BYTES) + rho * kP;
+          __nv_bfloat16* dst_lo = dst_hi + kVolPad;
+          uint32_t* ph = reinterpret_cast<uint32_t*>(dst_hi + (odd ? 1 : 0));
+          uint32_t* pl = reinterpret_cast<uint32_t*>(dst_lo + (odd ? 1 : 0));
+#pragma unroll
+          for (int j = 0; j < 24; ++j) {
+            uint32_t hi, lo;
+            split2(odd ? e[2 * j + 1] : e[2 * j], odd ? e[2 * j + 2] : e[2 * j + 1], hi, lo);
+            ph[j] = hi;
+            pl[j] = lo;
+          }
+          const bf16pair ed = split_bf16(odd ? e[0] : e[48]);
+          dst_hi[odd ? 0 : 48] = ed.hi;
+          dst_lo[odd ? 0 : 48] = ed.lo;
+        } else {
+          // K padding (elements 2401..2431 of the 4 planes) = zero: one 2-byte element + 15 aligned pairs per plane
+          for (int j = r - 2 * kP; j < 4 * 16; j += 128 - 2 * kP) {
+            __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(img) + (j >> 4) * kVolPad;
+            const int w = j & 15;
+            if (w == 0) plane[kVol] = __float2bfloat16(0.f);
+            else *reinterpret_cast<uint32_t*>(plane + kVol - 1 + 2 * w) = 0u;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // ---- coalesced copy-out of whole volume rows
+        for (int idx = r; idx < 2 * (ROW_BYTES / 16); idx += 128) {
+          const int ff = idx >= ROW_BYTES / 16 ? 1 : 0, w16 = idx - ff * (ROW_BYTES / 16);
+          const int t = 2 * tp + ff;
+          if (t < g.T) {
+            uint4* grow = reinterpret_cast<uint4*>(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad));
+            grow[w16] = reinterpret_cast<const uint4*>(img + ff * ROW_BYTES)[w16];
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // image read: the next tile may write h
       }
     }
   }
