@@ -19,7 +19,7 @@
 //   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
 //             row -> shared [row][a][k] (16-byte vectors) -> y-blend in registers, one thread per volume row ->
 //             split-bf16 byte image of the two 9728-byte volume rows (reusing the blend buffer, K padding zero)
-//             -> fully coalesced 16-byte stores
+//             -> one bulk shared->global copy (TMA engine) per 9728-byte volume row
 // Warps: 0 TMA issuer, 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -266,6 +266,8 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         // ---- x-blend: h[row][a][k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k], 4 k per shared-memory store
         float v[32];
         tmem_ld32(taddr, v);                       // columns 0..31
+        if (r == 0) bulk_wait_read0();             // previous tile's image has left shared memory ...
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ... so h may be written again
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           float hv[4];
@@ -343,21 +345,24 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
             else *reinterpret_cast<uint32_t*>(plane + kVol - 1 + 2 * w) = 0u;
           }
         }
+        fence_proxy_async_smem();                   // image writes -> visible to the bulk-copy (async proxy) reads
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        // ---- coalesced copy-out of whole volume rows
-        for (int idx = r; idx < 2 * (ROW_BYTES / 16); idx += 128) {
-          const int ff = idx >= ROW_BYTES / 16 ? 1 : 0, w16 = idx - ff * (ROW_BYTES / 16);
-          const int t = 2 * tp + ff;
-          if (t < g.T) {
-            uint4* grow = reinterpret_cast<uint4*>(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad));
-            grow[w16] = reinterpret_cast<const uint4*>(img + ff * ROW_BYTES)[w16];
+        // ---- copy-out: one bulk shared->global copy per volume row (9728 contiguous bytes), issued by one thread;
+        // its shared-memory reads are awaited just before the next tile of this group overwrites the buffer
+        if (r == 0) {
+#pragma unroll
+          for (int ff = 0; ff < 2; ++ff) {
+            const int t = 2 * tp + ff;
+            if (t < g.T)
+              bulk_store_s2g(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad), img + ff * ROW_BYTES, ROW_BYTES);
           }
+          bulk_commit();
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // image read: the next tile may write h
       }
     }
   }
 
+  if (warp >= EPI_WARP0 && (threadIdx.x & 127) == 0) bulk_wait0();   // outstanding volume-row copies
   tc_fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
