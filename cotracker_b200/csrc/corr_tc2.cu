@@ -13,7 +13,9 @@
 //
 //   pyramid : a split-bf16 copy [level][plane hi|lo][T][H][W][128] made once per update-loop call
 //   A tile  [128 x 128] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, plane, K-half) is ONE 4-D
-//             TMA box (64 ch x 8 x 8 x 1) landing directly in the 128B-swizzled K-major operand layout; 2 stages
+//             TMA box (64 ch x 8 x 8 x 1) landing directly in the 128B-swizzled K-major operand layout; the ring
+//             holds 4 K-half slots (32 KiB: hi|lo x 2 frames), freed as soon as their 12 MMAs retire -- the loop is
+//             bound by TMA latency x bytes in flight, so slot granularity matters more than MMA rate
 //   B tile  [ 64 x 128] : the 49 support vectors of (n,l), split-bf16, built once per unit by 2 warps
 //   D       [128 x  64] : fp32 in TMEM, 3 tcgen05.mma per k16 step (lo*hi + hi*lo + hi*hi), 2 accumulators
 //   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
@@ -32,8 +34,9 @@ constexpr int MMA_WARP = 1;
 constexpr int SB_WARP0 = 2;               // 2 support-builder warps
 constexpr int EPI_WARP0 = 4;              // warps 4..7 group 0, 8..11 group 1; (warp & 3) = TMEM lane quarter
 constexpr int THREADS = 12 * 32;
-constexpr int A_PLANE = 2 * 16384;        // one bf16 plane of A: 2 K-halves x [128 rows x 128 B]
-constexpr int A_STAGE = 2 * A_PLANE;      // hi + lo = 64 KiB
+constexpr int NSLOT = 4;                  // A ring: slots of one K-half (64 channels) of a 2-frame tile
+constexpr int A_PLANE = 16384;            // one bf16 plane of a slot: [128 rows x 128 B]
+constexpr int A_SLOT = 2 * A_PLANE;       // hi + lo = 32 KiB
 constexpr int S_PART = 2 * 8192;          // one plane of S: 2 K-halves x [64 rows x 128 B]
 constexpr int S_BYTES = 2 * S_PART;       // 32 KiB
 constexpr int H_A = 52;                   // floats per (texel row, a): 49 + pad, keeps every vector 16-byte aligned
@@ -43,7 +46,7 @@ constexpr int H_GROUP = 2 * H_FRAME * 4;  // bytes per epilogue group (2 frames)
 constexpr int ROW_BYTES = 2 * kVolPad * 2;   // 9728: one volume row image [hi | lo]
 static_assert(2 * ROW_BYTES <= H_GROUP, "the output image of a tile reuses the blend buffer");
 constexpr int OFF_A = 0;
-constexpr int OFF_S = OFF_A + 2 * A_STAGE;
+constexpr int OFF_S = OFF_A + NSLOT * A_SLOT;
 constexpr int OFF_H = OFF_S + S_BYTES;
 constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*H_ROW, row1*H_ROW, -}
 constexpr int OFF_PARAM = OFF_TAB + 2 * 2 * 8 * 16;  // [slot 4][frame 2] x {cx, cy, box_x, box_y}
@@ -88,13 +91,13 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* a_full = bars;          // [2] TMA -> MMA             (count 1 + tx bytes)
-  uint64_t* a_empty = bars + 2;     // [2] MMA -> TMA             (tcgen05.commit)
-  uint64_t* d_full = bars + 4;      // [2] MMA -> epilogue group  (tcgen05.commit)
-  uint64_t* d_empty = bars + 6;     // [2] epilogue group -> MMA  (count 4)
-  uint64_t* s_full = bars + 8;      // builders -> MMA, per unit  (count 2)
-  uint64_t* s_empty = bars + 9;     // MMA -> builders, per unit  (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* a_full = bars;                  // [NSLOT] TMA -> MMA         (count 1 + tx bytes)
+  uint64_t* a_empty = bars + NSLOT;         // [NSLOT] MMA -> TMA         (tcgen05.commit)
+  uint64_t* d_full = bars + 2 * NSLOT;      // [2] MMA -> epilogue group  (tcgen05.commit)
+  uint64_t* d_empty = bars + 2 * NSLOT + 2; // [2] epilogue group -> MMA  (count 4)
+  uint64_t* s_full = bars + 2 * NSLOT + 4;  // builders -> MMA, per unit  (count 2)
+  uint64_t* s_empty = bars + 2 * NSLOT + 5; // MMA -> builders, per unit  (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_unit = (g.T + 1) / 2;
@@ -103,9 +106,11 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
   for (int i = threadIdx.x; i < S_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_S)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 4);
     }
@@ -122,7 +127,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
 
   if (warp == TMA_WARP) {
     // ================================================================== TMA issuer (whole warp walks, lane 0 issues)
-    uint32_t it = 0;
+    uint32_t it = 0, hc = 0;   // tile / K-half slot counters
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int n = u / kL, l = u % kL;
       const int H = g.lay.h[l], W = g.lay.w[l];
@@ -138,33 +143,28 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           const float cx1 = __shfl_sync(0xffffffffu, c.x, k1) * inv, cy1 = __shfl_sync(0xffffffffu, c.y, k1) * inv;
           if (lane == 0) {
             const int nf = (k + 1 < cnt) ? 2 : 1;
-            const int st = it & 1;
-            mbar_wait(&a_empty[st], ((it >> 1) & 1u) ^ 1u);
             const int bx0 = box_origin8(cx0, W), by0 = box_origin8(cy0, H);
             const int bx1 = box_origin8(cx1, W), by1 = box_origin8(cy1, H);
-            float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it & 3) * 32);
-            prm[0] = make_float4(cx0, cy0, __int_as_float(bx0), __int_as_float(by0));
-            prm[1] = make_float4(cx1, cy1, __int_as_float(bx1), __int_as_float(by1));
-#ifdef CT3_KO_TMA
-            mbar_arrive_expect_tx(&a_full[st], (uint32_t)(nf * (A_STAGE / 4)));
-#else
-            mbar_arrive_expect_tx(&a_full[st], (uint32_t)(nf * (A_STAGE / 2)));
-#endif
-            uint8_t* dst = smem + OFF_A + st * A_STAGE;
 #pragma unroll
-            for (int f = 0; f < 2; ++f) {
-              if (f < nf) {
-                const int bx = f ? bx1 : bx0, by = f ? by1 : by0;
+            for (int kh = 0; kh < 2; ++kh, ++hc) {
+              const int sl = hc % NSLOT;
+              mbar_wait(&a_empty[sl], ((hc / NSLOT) & 1u) ^ 1u);
+              if (kh == 0) {   // the tile's parameters become visible to the epilogue through a_full -> d_full
+                float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it & 3) * 32);
+                prm[0] = make_float4(cx0, cy0, __int_as_float(bx0), __int_as_float(by0));
+                prm[1] = make_float4(cx1, cy1, __int_as_float(bx1), __int_as_float(by1));
+              }
+              mbar_arrive_expect_tx(&a_full[sl], (uint32_t)(nf * (A_SLOT / 2)));
+              uint8_t* dst = smem + OFF_A + sl * A_SLOT;
 #pragma unroll
-#ifdef CT3_KO_TMA
-                for (int pl = 0; pl < 1; ++pl)
-#else
-                for (int pl = 0; pl < 2; ++pl)
-#endif
+              for (int f = 0; f < 2; ++f) {
+                if (f < nf) {
+                  const int bx = f ? bx1 : bx0, by = f ? by1 : by0;
 #pragma unroll
-                  for (int kh = 0; kh < 2; ++kh)
-                    tma_load_4d(dst + pl * A_PLANE + kh * 16384 + f * 8192, &maps.m[l], kh * 64, bx, by,
-                                pl * g.T + t0 + k + f, &a_full[st]);
+                  for (int pl = 0; pl < 2; ++pl)
+                    tma_load_4d(dst + pl * A_PLANE + f * 8192, &maps.m[l], kh * 64, bx, by, pl * g.T + t0 + k + f,
+                                &a_full[sl]);
+                }
               }
             }
           }
@@ -176,33 +176,32 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
     // ================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      uint32_t it = 0, ui = 0;
+      uint32_t it = 0, ui = 0, hc = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);
       for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
         mbar_wait(s_full, ui & 1u);
         for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
-          const int st = it & 1;
-          mbar_wait(&a_full[st], (it >> 1) & 1u);
-          mbar_wait(&d_empty[st], ((it >> 1) & 1u) ^ 1u);
-          tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(st * 64);
-          const uint32_t a_base = smem_u32(smem + OFF_A + st * A_STAGE);
+          const int acc = it & 1;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t ao = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
-            const uint32_t so = (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32);
-            const uint64_t dah = umma_desc_sw128(a_base + ao), dal = umma_desc_sw128(a_base + A_PLANE + ao);
-            const uint64_t dsh = umma_desc_sw128(s_base + so), dsl = umma_desc_sw128(s_base + S_PART + so);
-#ifdef CT3_KO_MMA
-            umma_bf16(d_tmem, dah, dsh, idesc, ks != 0 ? 1u : 0u);
-#else
-            umma_bf16(d_tmem, dal, dsh, idesc, ks != 0 ? 1u : 0u);
-            umma_bf16(d_tmem, dah, dsl, idesc, 1u);
-            umma_bf16(d_tmem, dah, dsh, idesc, 1u);
-#endif
+          for (int kh = 0; kh < 2; ++kh, ++hc) {
+            const int sl = hc % NSLOT;
+            mbar_wait(&a_full[sl], (hc / NSLOT) & 1u);
+            if (kh == 0) mbar_wait(&d_empty[acc], ((it >> 1) & 1u) ^ 1u);
+            tc_fence_after_sync();
+            const uint32_t a_base = smem_u32(smem + OFF_A + sl * A_SLOT);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t so = (uint32_t)(kh * 8192 + j * 32);
+              const uint64_t dah = umma_desc_sw128(a_base + j * 32), dal = umma_desc_sw128(a_base + A_PLANE + j * 32);
+              const uint64_t dsh = umma_desc_sw128(s_base + so), dsl = umma_desc_sw128(s_base + S_PART + so);
+              umma_bf16(d_tmem, dal, dsh, idesc, (kh | j) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, dah, dsl, idesc, 1u);
+              umma_bf16(d_tmem, dah, dsh, idesc, 1u);
+            }
+            umma_commit(&a_empty[sl]);   // this K-half may be refilled while the other one is still being multiplied
           }
-          umma_commit(&a_empty[st]);
-          umma_commit(&d_full[st]);
+          umma_commit(&d_full[acc]);
         }
         umma_commit(s_empty);
       }
@@ -278,14 +277,6 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         // ---- x-blend: h[row][a][k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k], 4 k per shared-memory store
         float v[32];
         tmem_ld32(taddr, v);                       // columns 0..31
-#ifdef CT3_KO_EPI
-        tmem_ld32(taddr + 32, v);
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&d_empty[grp]);
-        if (v[3] == 1234.5f) hrow[0] = make_float4(v[0], v[1], v[2], v[3]);
-        continue;
-#endif
         if (r == 0) bulk_wait_read0();             // previous tile's image has left shared memory ...
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ... so h may be written again
 #pragma unroll
@@ -293,12 +284,8 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           float hv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-#ifdef CT3_KO_X
-            hv[j] = ux * v[4 * k4 + j];
-#else
             const float v0 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src0), v1 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src1);
             hv[j] = ux * v0 + wx * v1;
-#endif
           }
           if (px < 7) hrow[k4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
@@ -312,12 +299,8 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (4 * k4 + j < kP - 32) {
-#ifdef CT3_KO_X
-              hv[j] = ux * v[4 * k4 + j];
-#else
               const float v0 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src0), v1 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src1);
               hv[j] = ux * v0 + wx * v1;
-#endif
             }
           }
           if (px < 7) hrow[8 + k4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
@@ -331,12 +314,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         // ---- y-blend in registers: e[k] = (1-wy) h[row0][a][k] + wy h[row1][a][k] for this thread's volume row
         float e[H_A];
-#ifdef CT3_KO_Y
-        for (int k = 0; k < H_A; ++k) e[k] = prm.x + (float)k;
-        if (false) {
-#else
         if (yrow) {
-#endif
           const float4 tb = tab[yf * 8 + yb];
           const float4* h0 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.y));
           const float4* h1 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.z));
@@ -352,11 +330,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         }
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // h fully read: the image may overwrite it
         // ---- split-bf16 byte image of the tile's two volume rows ([hi(2432) | lo(2432)] each)
-#ifdef CT3_KO_IMG
-        if (yrow && e[7] == 1234.5f) {
-#else
         if (yrow) {
-#endif
           // 49 bf16 per plane at element offset rho*49: one 2-byte edge element (the first if that offset is odd,
           // else the last) + 24 aligned 4-byte pairs
           __nv_bfloat16* dst_hi = reinterpret_cast<__nv_bfloat16*>(img + yf * ROW_BYTES) + rho * kP;
@@ -386,11 +360,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         // ---- copy-out: one bulk shared->global copy per volume row (9728 contiguous bytes), issued by one thread;
         // its shared-memory reads are awaited just before the next tile of this group overwrites the buffer
-#ifdef CT3_KO_BULK
-        if (r == 0 && prm.x == 1234.5f) {
-#else
         if (r == 0) {
-#endif
 #pragma unroll
           for (int ff = 0; ff < 2; ++ff) {
             const int t = 2 * tp + ff;
