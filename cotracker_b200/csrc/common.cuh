@@ -138,6 +138,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Dynamic shared memory base rounded up to 1024 B WITHOUT leaving the shared address space (an integer round trip
 // through uintptr_t turns every later access into a generic LD/ST).
+// Spinning variant for single-thread waiters on a latency-critical chain (TMA / MMA issuers): no suspend hint,
+// so the thread observes the phase flip as soon as it happens.  Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 28)) asm volatile("trap;");
+  }
+}
 __device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
   return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
 }

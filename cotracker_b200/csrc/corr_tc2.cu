@@ -148,7 +148,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
 #pragma unroll
             for (int kh = 0; kh < 2; ++kh, ++hc) {
               const int sl = hc % NSLOT;
-              mbar_wait(&a_empty[sl], ((hc / NSLOT) & 1u) ^ 1u);
+              mbar_wait_spin(&a_empty[sl], ((hc / NSLOT) & 1u) ^ 1u);
               if (kh == 0) {   // the tile's parameters become visible to the epilogue through a_full -> d_full
                 float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it & 3) * 32);
                 prm[0] = make_float4(cx0, cy0, __int_as_float(bx0), __int_as_float(by0));
@@ -179,15 +179,15 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
       uint32_t it = 0, ui = 0, hc = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);
       for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
-        mbar_wait(s_full, ui & 1u);
+        mbar_wait_spin(s_full, ui & 1u);
         for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
           const int acc = it & 1;
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh, ++hc) {
             const int sl = hc % NSLOT;
-            mbar_wait(&a_full[sl], (hc / NSLOT) & 1u);
-            if (kh == 0) mbar_wait(&d_empty[acc], ((it >> 1) & 1u) ^ 1u);
+            mbar_wait_spin(&a_full[sl], (hc / NSLOT) & 1u);
+            if (kh == 0) mbar_wait_spin(&d_empty[acc], ((it >> 1) & 1u) ^ 1u);
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(smem + OFF_A + sl * A_SLOT);
 #pragma unroll
