@@ -62,7 +62,13 @@ struct Corr2Args {
   const float* coords;         // [T, N, 2]
   int T, N;
   __nv_bfloat16* vol;          // [N*T*4, 2*kVolPad]
+  long long* trace;            // CT3_TRACE builds: [256 tiles][8 events] clock64 of CTA 0
 };
+#ifdef CT3_TRACE
+#define TRACE(tile, ev) do { if (blockIdx.x == 0 && (tile) < 256) g.trace[(tile) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(tile, ev) do { } while (0)
+#endif
 struct Corr2Maps {
   CUtensorMap m[kL];           // per level: bf16 dims (128, W, H, 2T), box (64, 8, 8, 1), 128B swizzle
 };
@@ -148,7 +154,9 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
 #pragma unroll
             for (int kh = 0; kh < 2; ++kh, ++hc) {
               const int sl = hc % NSLOT;
+              if (kh == 0) TRACE(it, 0);
               mbar_wait_spin(&a_empty[sl], ((hc / NSLOT) & 1u) ^ 1u);
+              if (kh == 0) TRACE(it, 1);
               if (kh == 0) {   // the tile's parameters become visible to the epilogue through a_full -> d_full
                 float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it & 3) * 32);
                 prm[0] = make_float4(cx0, cy0, __int_as_float(bx0), __int_as_float(by0));
@@ -187,7 +195,9 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           for (int kh = 0; kh < 2; ++kh, ++hc) {
             const int sl = hc % NSLOT;
             mbar_wait_spin(&a_full[sl], (hc / NSLOT) & 1u);
+            if (kh == 0) TRACE(it, 2);
             if (kh == 0) mbar_wait_spin(&d_empty[acc], ((it >> 1) & 1u) ^ 1u);
+            if (kh == 0) TRACE(it, 3);
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(smem + OFF_A + sl * A_SLOT);
 #pragma unroll
@@ -202,6 +212,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
             umma_commit(&a_empty[sl]);   // this K-half may be refilled while the other one is still being multiplied
           }
           umma_commit(&d_full[acc]);
+          TRACE(it, 4);
         }
         umma_commit(s_empty);
       }
@@ -266,6 +277,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
       for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
         if ((int)(it & 1u) != grp) continue;
         mbar_wait(&d_full[grp], (it >> 1) & 1u);
+        if (r == 0) TRACE(it, 5);
         tc_fence_after_sync();
         const float4 prm = *reinterpret_cast<const float4*>(smem + OFF_PARAM + (it & 3) * 32 + f * 16);
         const int bx = __float_as_int(prm.z), by = __float_as_int(prm.w);
@@ -293,6 +305,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
+        if (r == 0) TRACE(it, 6);
 #pragma unroll
         for (int k4 = 0; k4 < 5; ++k4) {
           float hv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -368,6 +381,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
               bulk_store_s2g(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad), img + ff * ROW_BYTES, ROW_BYTES);
           }
           bulk_commit();
+          TRACE(it, 7);
         }
       }
     }
@@ -423,6 +437,12 @@ cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4,
   g.T = T;
   g.N = N;
   g.vol = vol_split;
+  g.trace = nullptr;
+#ifdef CT3_TRACE
+  static long long* trace_buf = nullptr;
+  if (!trace_buf) cudaMalloc(&trace_buf, 256 * 8 * sizeof(long long));
+  g.trace = trace_buf;
+#endif
   Corr2Maps maps;
   for (int l = 0; l < kL; ++l) {
     const uint64_t W = (uint64_t)g.lay.w[l], H = (uint64_t)g.lay.h[l];
@@ -443,6 +463,25 @@ cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4,
   const int num_units = N * kL;
   const int grid = num_units < num_sms ? num_units : num_sms;
   corr_patch_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
+#ifdef CT3_TRACE
+  {
+    static int calls = 0;
+    if (++calls == 3) {
+      cudaStreamSynchronize(s);
+      static long long h[256 * 8];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const char* nm[8] = {"tma_wait", "tma_go", "mma_afull", "mma_dempty", "mma_issued", "epi_dfull", "epi_dempty", "epi_end"};
+      printf("tile");
+      for (int e = 0; e < 8; ++e) printf(" %10s", nm[e]);
+      printf("\n");
+      for (int t = 32; t < 96; ++t) {
+        printf("%4d", t);
+        for (int e = 0; e < 8; ++e) printf(" %10lld", h[t * 8 + e] - h[32 * 8]);
+        printf("\n");
+      }
+    }
+  }
+#endif
   return cudaGetLastError();
 }
 
