@@ -23,6 +23,7 @@
 //             split-bf16 byte image of the two 9728-byte volume rows (reusing the blend buffer, K padding zero)
 //             -> one bulk shared->global copy (TMA engine) per 9728-byte volume row
 // Warps: 0 TMA issuer, 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
+#include <cstdio>
 #include "gemm.cuh"
 #include "kernels.cuh"
 
