@@ -19,7 +19,9 @@
 //   B tile  [ 64 x 128] : the 49 support vectors of (n,l), split-bf16, built once per unit by 2 warps
 //   D       [128 x  64] : fp32 in TMEM, 3 tcgen05.mma per k16 step (lo*hi + hi*lo + hi*hi), 2 accumulators
 //   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
-//             row -> shared [row][a][k] (16-byte vectors) -> y-blend in registers, one thread per volume row ->
+//             row -> y-blend: interior tiles entirely in registers (next texel row = 8 lanes up, texel row 4 crosses
+//             the warp boundary through a 3 KiB exchange buffer); tiles with a border clamp through a shared
+//             [row][a][k] buffer and a per-row tap table -> one thread per volume row ->
 //             split-bf16 byte image of the two 9728-byte volume rows (reusing the blend buffer, K padding zero)
 //             -> one bulk shared->global copy (TMA engine) per 9728-byte volume row
 // Warps: 0 TMA issuer, 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
@@ -50,7 +52,9 @@ constexpr int OFF_A = 0;
 constexpr int OFF_S = OFF_A + NSLOT * A_SLOT;
 constexpr int OFF_H = OFF_S + S_BYTES;
 constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*H_ROW, row1*H_ROW, -}
-constexpr int OFF_PARAM = OFF_TAB + 2 * 2 * 8 * 16;  // [slot 4][frame 2] x {cx, cy, box_x, box_y}
+constexpr int XCH_GROUP = 2 * 7 * H_A * 4;       // texel row 4 of both frames: [frame][a][k], register y-blend path
+constexpr int OFF_XCH = OFF_TAB + 2 * 2 * 8 * 16;
+constexpr int OFF_PARAM = OFF_XCH + 2 * XCH_GROUP;   // [slot 4][frame 2] x {cx, cy, box_x, box_y}
 constexpr int OFF_BAR = OFF_PARAM + 4 * 2 * 16;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -262,15 +266,20 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
     float* hbuf = reinterpret_cast<float*>(smem + OFF_H + grp * H_GROUP);
     uint8_t* img = smem + OFF_H + grp * H_GROUP;     // output image of the tile, reuses hbuf once it has been read
     float4* tab = reinterpret_cast<float4*>(smem + OFF_TAB + grp * 256);
+    float4* xch = reinterpret_cast<float4*>(smem + OFF_XCH + grp * XCH_GROUP);
     float4* hrow = reinterpret_cast<float4*>(hbuf + f * H_FRAME + py * H_ROW + a * H_A);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 64);
     const int bar_id = 1 + grp;
-    // y-blend role: thread r < 98 owns volume row (frame yf, sample rho = ya*7 + yb) of the tile
-    const bool yrow = r < 2 * kP;
+    // volume row owned by this thread when the y-blend runs ...
+    //   in registers (interior tiles): lane (texel row b = py < 7, a = px < 7) of frame f -> rho = a*7 + b
+    const bool own_fast = px < 7 && py < 7;
+    const int rho_fast = px * 7 + py;
+    const int idle_fast = f * 15 + (py < 7 ? py : 7 + px);   // 0..29 among the 30 threads without a row
+    //   through shared memory (tiles touching a border): thread r < 98 -> frame r / 49, rho = r % 49
+    const bool own_gen = r < 2 * kP;
     const int yf = r >= kP ? 1 : 0;
-    const int rho = r - yf * kP;
-    const int ya = rho / 7, yb = rho - ya * 7;
-    const bool odd = (rho & 1) != 0;
+    const int rho_gen = r - yf * kP;
+    const int ya = rho_gen / 7, yb = rho_gen - ya * 7;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int n = u / kL, l = u % kL;
@@ -280,27 +289,33 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         mbar_wait(&d_full[grp], (it >> 1) & 1u);
         if (r == 0) TRACE(it, 5);
         tc_fence_after_sync();
-        const float4 prm = *reinterpret_cast<const float4*>(smem + OFF_PARAM + (it & 3) * 32 + f * 16);
-        const int bx = __float_as_int(prm.z), by = __float_as_int(prm.w);
+        const float4* prms = reinterpret_cast<const float4*>(smem + OFF_PARAM + (it & 3) * 32);
+        const float4 prm = prms[f];
         int sx0, sx1;
         float wx;
-        tap_pair(prm.x, a - kR, W, bx, sx0, sx1, wx);
+        tap_pair(prm.x, a - kR, W, __float_as_int(prm.z), sx0, sx1, wx);
         const float ux = 1.f - wx;
         const int src0 = (lane & 24) | sx0, src1 = (lane & 24) | sx1;
-        // ---- x-blend: h[row][a][k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k], 4 k per shared-memory store
+        // y taps of sample row b = lane & 7 of frame (lane >> 3) & 1, evaluated by lanes 0..6 / 8..14 of every warp.
+        // Interior tile (both frames): sample row b blends texel rows b and b+1 of the box -> y-blend in registers.
+        float wy_l;
+        int r0_l, r1_l;
+        {
+          const float4 pq = prms[(lane >> 3) & 1];
+          const int b = lane & 7;
+          tap_pair(pq.y, min(b, 6) - kR, H, __float_as_int(pq.w), r0_l, r1_l, wy_l);
+        }
+        const bool ok_l = (lane & 7) == 7 || (r0_l == (lane & 7) && r1_l == (lane & 7) + (wy_l > 0.f ? 1 : 0));
+        const bool fast = (__ballot_sync(0xffffffffu, ok_l) & 0xffffu) == 0xffffu;
+        const float wy = __shfl_sync(0xffffffffu, wy_l, f * 8 + min(py, 6));   // this lane's row weight (fast path)
+        // ---- x-blend: h[k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k]  for (texel row py, sample column a)
+        float h[H_A];
         float v[32];
         tmem_ld32(taddr, v);                       // columns 0..31
-        if (r == 0) bulk_wait_read0();             // previous tile's image has left shared memory ...
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ... so h may be written again
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          float hv[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float v0 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src0), v1 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src1);
-            hv[j] = ux * v0 + wx * v1;
-          }
-          if (px < 7) hrow[k4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        for (int k = 0; k < 32; ++k) {
+          const float v0 = __shfl_sync(0xffffffffu, v[k], src0), v1 = __shfl_sync(0xffffffffu, v[k], src1);
+          h[k] = ux * v0 + wx * v1;
         }
         tmem_ld32(taddr + 32, v);                  // columns 32..63 (32..48 used)
         tc_fence_before_sync();
@@ -308,62 +323,95 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
         if (r == 0) TRACE(it, 6);
 #pragma unroll
-        for (int k4 = 0; k4 < 5; ++k4) {
-          float hv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (4 * k4 + j < kP - 32) {
-              const float v0 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src0), v1 = __shfl_sync(0xffffffffu, v[4 * k4 + j], src1);
-              hv[j] = ux * v0 + wx * v1;
-            }
+        for (int k = 32; k < H_A; ++k) {
+          h[k] = 0.f;
+          if (k < kP) {
+            const float v0 = __shfl_sync(0xffffffffu, v[k - 32], src0), v1 = __shfl_sync(0xffffffffu, v[k - 32], src1);
+            h[k] = ux * v0 + wx * v1;
           }
-          if (px < 7) hrow[8 + k4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
-        if ((r & 63) < 7) {                         // y taps of sample row b, shared by the whole frame
-          int r0, r1;
-          float wy;
-          tap_pair(prm.y, (r & 63) - kR, H, by, r0, r1, wy);
-          tab[f * 8 + (r & 63)] = make_float4(wy, __int_as_float(r0 * H_ROW), __int_as_float(r1 * H_ROW), 0.f);
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        // ---- y-blend in registers: e[k] = (1-wy) h[row0][a][k] + wy h[row1][a][k] for this thread's volume row
-        float e[H_A];
-        if (yrow) {
-          const float4 tb = tab[yf * 8 + yb];
-          const float4* h0 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.y));
-          const float4* h1 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.z));
-          const float wy = tb.x, uy = 1.f - tb.x;
+        bool own;
+        int ff, rho;
+        if (fast) {
+          // ---- y-blend in registers: the next texel row is 8 lanes up; texel row 4 (first row of the odd warp)
+          // reaches the even warp's last row through a small exchange buffer
+          if ((q & 1) && lane < 7) {
+#pragma unroll
+            for (int k4 = 0; k4 < H_A / 4; ++k4)
+              xch[(f * 7 + lane) * (H_A / 4) + k4] = make_float4(h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
+          }
+          if (r == 0) bulk_wait_read0();           // previous tile's image has left shared memory
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          const bool edge = !(q & 1) && (lane >> 3) == 3 && px < 7;   // texel row 3: its lower neighbour is row 4
+          const float uy = 1.f - wy;
 #pragma unroll
           for (int k4 = 0; k4 < H_A / 4; ++k4) {
-            const float4 p0 = h0[k4], p1 = h1[k4];
-            e[4 * k4 + 0] = uy * p0.x + wy * p1.x;
-            e[4 * k4 + 1] = uy * p0.y + wy * p1.y;
-            e[4 * k4 + 2] = uy * p0.z + wy * p1.z;
-            e[4 * k4 + 3] = uy * p0.w + wy * p1.w;
+            float4 dn;
+            dn.x = __shfl_down_sync(0xffffffffu, h[4 * k4 + 0], 8);
+            dn.y = __shfl_down_sync(0xffffffffu, h[4 * k4 + 1], 8);
+            dn.z = __shfl_down_sync(0xffffffffu, h[4 * k4 + 2], 8);
+            dn.w = __shfl_down_sync(0xffffffffu, h[4 * k4 + 3], 8);
+            if (edge) dn = xch[(f * 7 + px) * (H_A / 4) + k4];
+            h[4 * k4 + 0] = uy * h[4 * k4 + 0] + wy * dn.x;
+            h[4 * k4 + 1] = uy * h[4 * k4 + 1] + wy * dn.y;
+            h[4 * k4 + 2] = uy * h[4 * k4 + 2] + wy * dn.z;
+            h[4 * k4 + 3] = uy * h[4 * k4 + 3] + wy * dn.w;
           }
+          own = own_fast;
+          ff = f;
+          rho = rho_fast;
+        } else {
+          // ---- y-blend through shared memory (any border clamp): [texel row][a][k] buffer + per-row tap table
+          if (r == 0) bulk_wait_read0();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // image of the previous tile is gone
+          if (px < 7) {
+#pragma unroll
+            for (int k4 = 0; k4 < H_A / 4; ++k4) hrow[k4] = make_float4(h[4 * k4], h[4 * k4 + 1], h[4 * k4 + 2], h[4 * k4 + 3]);
+          }
+          if (q == 0 && lane < 16 && (lane & 7) < 7)   // one writer per (frame lane >> 3, sample row b = lane & 7)
+            tab[(lane >> 3) * 8 + (lane & 7)] = make_float4(wy_l, __int_as_float(r0_l * H_ROW), __int_as_float(r1_l * H_ROW), 0.f);
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (own_gen) {
+            const float4 tb = tab[yf * 8 + yb];
+            const float4* h0 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.y));
+            const float4* h1 = reinterpret_cast<const float4*>(hbuf + yf * H_FRAME + ya * H_A + __float_as_int(tb.z));
+            const float wyg = tb.x, uyg = 1.f - tb.x;
+#pragma unroll
+            for (int k4 = 0; k4 < H_A / 4; ++k4) {
+              const float4 p0 = h0[k4], p1 = h1[k4];
+              h[4 * k4 + 0] = uyg * p0.x + wyg * p1.x;
+              h[4 * k4 + 1] = uyg * p0.y + wyg * p1.y;
+              h[4 * k4 + 2] = uyg * p0.z + wyg * p1.z;
+              h[4 * k4 + 3] = uyg * p0.w + wyg * p1.w;
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // h fully read: the image may overwrite it
+          own = own_gen;
+          ff = yf;
+          rho = rho_gen;
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // h fully read: the image may overwrite it
         // ---- split-bf16 byte image of the tile's two volume rows ([hi(2432) | lo(2432)] each)
-        if (yrow) {
+        if (own) {
           // 49 bf16 per plane at element offset rho*49: one 2-byte edge element (the first if that offset is odd,
           // else the last) + 24 aligned 4-byte pairs
-          __nv_bfloat16* dst_hi = reinterpret_cast<__nv_bfloat16*>(img + yf * ROW_BYTES) + rho * kP;
+          const bool odd = (rho & 1) != 0;
+          __nv_bfloat16* dst_hi = reinterpret_cast<__nv_bfloat16*>(img + ff * ROW_BYTES) + rho * kP;
           __nv_bfloat16* dst_lo = dst_hi + kVolPad;
           uint32_t* ph = reinterpret_cast<uint32_t*>(dst_hi + (odd ? 1 : 0));
           uint32_t* pl = reinterpret_cast<uint32_t*>(dst_lo + (odd ? 1 : 0));
 #pragma unroll
           for (int j = 0; j < 24; ++j) {
             uint32_t hi, lo;
-            split2(odd ? e[2 * j + 1] : e[2 * j], odd ? e[2 * j + 2] : e[2 * j + 1], hi, lo);
+            split2(odd ? h[2 * j + 1] : h[2 * j], odd ? h[2 * j + 2] : h[2 * j + 1], hi, lo);
             ph[j] = hi;
             pl[j] = lo;
           }
-          const bf16pair ed = split_bf16(odd ? e[0] : e[48]);
+          const bf16pair ed = split_bf16(odd ? h[0] : h[48]);
           dst_hi[odd ? 0 : 48] = ed.hi;
           dst_lo[odd ? 0 : 48] = ed.lo;
         } else {
           // K padding (elements 2401..2431 of the 4 planes) = zero: one 2-byte element + 15 aligned pairs per plane
-          for (int j = r - 2 * kP; j < 4 * 16; j += 128 - 2 * kP) {
+          for (int j = fast ? idle_fast : r - 2 * kP; j < 4 * 16; j += 128 - 2 * kP) {
             __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(img) + (j >> 4) * kVolPad;
             const int w = j & 15;
             if (w == 0) plane[kVol] = __float2bfloat16(0.f);
@@ -373,13 +421,13 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         fence_proxy_async_smem();                   // image writes -> visible to the bulk-copy (async proxy) reads
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         // ---- copy-out: one bulk shared->global copy per volume row (9728 contiguous bytes), issued by one thread;
-        // its shared-memory reads are awaited just before the next tile of this group overwrites the buffer
+        // its shared-memory reads are awaited before the next tile of this group touches the buffer
         if (r == 0) {
 #pragma unroll
-          for (int ff = 0; ff < 2; ++ff) {
-            const int t = 2 * tp + ff;
+          for (int t2 = 0; t2 < 2; ++t2) {
+            const int t = 2 * tp + t2;
             if (t < g.T)
-              bulk_store_s2g(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad), img + ff * ROW_BYTES, ROW_BYTES);
+              bulk_store_s2g(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad), img + t2 * ROW_BYTES, ROW_BYTES);
           }
           bulk_commit();
           TRACE(it, 7);
