@@ -156,6 +156,20 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 28)) asm volatile("trap;");
   }
 }
+// elect.sync: true in exactly one lane of a converged warp.  Unlike `lane == 0`, ptxas knows the guarded region
+// runs with a single active thread and keeps tcgen05/TMA operands in uniform registers (no per-instruction
+// ELECT/BRA.U.ANY waterfall loop around every UTCHMMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
   return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
 }

@@ -267,7 +267,7 @@ corr_sample_tc_kernel(const __grid_constant__ CorrTcArgs g, const __grid_constan
     }
   } else if (warp == MMA_WARP) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       uint32_t it = 0, ui = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);

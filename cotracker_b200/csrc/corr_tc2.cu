@@ -152,7 +152,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           const int k1 = min(k + 1, 31);
           const float cx0 = __shfl_sync(0xffffffffu, c.x, k) * inv, cy0 = __shfl_sync(0xffffffffu, c.y, k) * inv;
           const float cx1 = __shfl_sync(0xffffffffu, c.x, k1) * inv, cy1 = __shfl_sync(0xffffffffu, c.y, k1) * inv;
-          if (lane == 0) {
+          if (elect_one()) {
             const int nf = (k + 1 < cnt) ? 2 : 1;
             const int bx0 = box_origin8(cx0, W), by0 = box_origin8(cy0, H);
             const int bx1 = box_origin8(cx1, W), by1 = box_origin8(cy1, H);
@@ -187,7 +187,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
     }
   } else if (warp == MMA_WARP) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
       uint32_t it = 0, ui = 0, hc = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);

@@ -161,7 +161,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -180,7 +180,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -294,7 +294,7 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first; tile < num_tiles; tile += step) {
@@ -314,7 +314,7 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BNP);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
