@@ -286,7 +286,7 @@ def main():
                      "note": "algorithmic fp32-equivalent FLOPs; each is 3 bf16 tensor-core products, so the "
                              "tensor pipe is busy at 3x this fraction; peak = sustained cuBLAS bf16 (" + pk["source"] + ")",
                      "ms_per_step": cat_ms["gemm"], "launches_per_step": cat_n["gemm"]},
-        "roofline_corr": {"kernel": "corr_sample", "bound": "hbm", "achieved": corr_gbs, "peak": pk["hbm"],
+        "roofline_corr": {"kernel": "corr_patch_tc_kernel (corr_tc2.cu; fused sampling + 4-D correlation)", "bound": "hbm", "achieved": corr_gbs, "peak": pk["hbm"],
                           "unit": "GB/s", "frac": corr_gbs / pk["hbm"],
                           "traffic": traffic.get("corr_sample", {}).get("dram_bytes_per_step"),
                           "algorithmic_bytes_per_step": corr_bytes,
