@@ -16,8 +16,10 @@
 //             TMA box (64 ch x 8 x 8 x 1) landing directly in the 128B-swizzled K-major operand layout; the ring
 //             holds 4 K-half slots (32 KiB: hi|lo x 2 frames), freed as soon as their 12 MMAs retire -- the loop is
 //             bound by TMA latency x bytes in flight, so slot granularity matters more than MMA rate
-//   B tile  [ 64 x 128] : the 49 support vectors of (n,l), split-bf16, built once per unit by 2 warps
-//   D       [128 x  64] : fp32 in TMEM, 3 tcgen05.mma per k16 step (lo*hi + hi*lo + hi*hi), 2 accumulators
+//   B tile  [128 x 128] : rows 0..63 hi plane / 64..127 lo plane of the 49 support vectors of (n,l) (rows 49..63
+//             of each plane zero), built once per unit by 2 warps
+//   D       [128 x 128] : fp32 in TMEM, 2 tcgen05.mma per k16 step: A_hi x [S_hi ; S_lo] (N=128, A_hi fetched once
+//             for both products) and A_lo x S_hi (N=64); the epilogue adds columns k and 64+k; 2 accumulators
 //   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
 //             row -> y-blend: interior tiles entirely in registers (next texel row = 8 lanes up, texel row 4 crosses
 //             the warp boundary through a 3 KiB exchange buffer); tiles with a border clamp through a shared
@@ -40,8 +42,8 @@ constexpr int THREADS = 12 * 32;
 constexpr int NSLOT = 4;                  // A ring: slots of one K-half (64 channels) of a 2-frame tile
 constexpr int A_PLANE = 16384;            // one bf16 plane of a slot: [128 rows x 128 B]
 constexpr int A_SLOT = 2 * A_PLANE;       // hi + lo = 32 KiB
-constexpr int S_PART = 2 * 8192;          // one plane of S: 2 K-halves x [64 rows x 128 B]
-constexpr int S_BYTES = 2 * S_PART;       // 32 KiB
+constexpr int S_HALF = 2 * 8192;          // one K-half of S: [hi rows 0..63 | lo rows 64..127] x 128 B = one N=128 operand
+constexpr int S_BYTES = 2 * S_HALF;       // 32 KiB
 constexpr int H_A = 52;                   // floats per (texel row, a): 49 + pad, keeps every vector 16-byte aligned
 constexpr int H_ROW = 7 * H_A;            // floats per texel row
 constexpr int H_FRAME = 8 * H_ROW;        // floats: x-blended correlations [row 8][a 7][k 52] of one frame
@@ -58,7 +60,7 @@ constexpr int OFF_PARAM = OFF_XCH + 2 * XCH_GROUP;   // [slot 4][frame 2] x {cx,
 constexpr int OFF_BAR = OFF_PARAM + 4 * 2 * 16;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-constexpr uint32_t TMEM_COLS = 128;       // 2 accumulators x 64 columns
+constexpr uint32_t TMEM_COLS = 256;       // 2 accumulators x (64 columns A*S_hi | 64 columns A_hi*S_lo)
 
 struct Corr2Args {
   PyramidLayout lay;
@@ -188,14 +190,14 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
   } else if (warp == MMA_WARP) {
     // ================================================================== MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64), idesc128 = umma_idesc_bf16(128, 128);
       uint32_t it = 0, ui = 0, hc = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);
       for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
         mbar_wait_spin(s_full, ui & 1u);
         for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
           const int acc = it & 1;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh, ++hc) {
             const int sl = hc % NSLOT;
@@ -207,12 +209,12 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
             const uint32_t a_base = smem_u32(smem + OFF_A + sl * A_SLOT);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t so = (uint32_t)(kh * 8192 + j * 32);
+              // A_hi x [S_hi ; S_lo] as ONE N=128 MMA (A_hi is fetched once for both products): columns 0..63 += A_hi S_hi,
+              // columns 64..127 += A_hi S_lo; then A_lo x S_hi (N=64) on columns 0..63.  The epilogue adds the halves.
               const uint64_t dah = umma_desc_sw128(a_base + j * 32), dal = umma_desc_sw128(a_base + A_PLANE + j * 32);
-              const uint64_t dsh = umma_desc_sw128(s_base + so), dsl = umma_desc_sw128(s_base + S_PART + so);
-              umma_bf16(d_tmem, dal, dsh, idesc, (kh | j) != 0 ? 1u : 0u);
-              umma_bf16(d_tmem, dah, dsl, idesc, 1u);
-              umma_bf16(d_tmem, dah, dsh, idesc, 1u);
+              const uint64_t ds = umma_desc_sw128(s_base + (uint32_t)(kh * S_HALF + j * 32));
+              umma_bf16(d_tmem, dah, ds, idesc128, (kh | j) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, dal, ds, idesc64, 1u);
             }
             umma_commit(&a_empty[sl]);   // this K-half may be refilled while the other one is still being multiplied
           }
@@ -247,9 +249,9 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           uint32_t h0, l0, h1, l1;
           split2(rows[j].x, rows[j].y, h0, l0);
           split2(rows[j].z, rows[j].w, h1, l1);
-          const uint32_t off = (uint32_t)(atom * 8192) + sw128(p, chunk) + (uint32_t)(half * 8);
-          *reinterpret_cast<uint2*>(s_hi + off) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(s_hi + S_PART + off) = make_uint2(l0, l1);
+          const uint32_t off = (uint32_t)(atom * S_HALF) + sw128(p, chunk) + (uint32_t)(half * 8);
+          *reinterpret_cast<uint2*>(s_hi + off) = make_uint2(h0, h1);          // rows 0..63 of the K-half: hi plane
+          *reinterpret_cast<uint2*>(s_hi + 8192 + off) = make_uint2(l0, l1);   // rows 64..127: lo plane
         }
       }
       fence_proxy_async_smem();
@@ -268,7 +270,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
     float4* tab = reinterpret_cast<float4*>(smem + OFF_TAB + grp * 256);
     float4* xch = reinterpret_cast<float4*>(smem + OFF_XCH + grp * XCH_GROUP);
     float4* hrow = reinterpret_cast<float4*>(hbuf + f * H_FRAME + py * H_ROW + a * H_A);
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 64);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
     const int bar_id = 1 + grp;
     // volume row owned by this thread when the y-blend runs ...
     //   in registers (interior tiles): lane (texel row b = py < 7, a = px < 7) of frame f -> rho = a*7 + b
@@ -310,24 +312,27 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         const float wy = __shfl_sync(0xffffffffu, wy_l, f * 8 + min(py, 6));   // this lane's row weight (fast path)
         // ---- x-blend: h[k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k]  for (texel row py, sample column a)
         float h[H_A];
-        float v[32];
-        tmem_ld32(taddr, v);                       // columns 0..31
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v0 = __shfl_sync(0xffffffffu, v[k], src0), v1 = __shfl_sync(0xffffffffu, v[k], src1);
-          h[k] = ux * v0 + wx * v1;
-        }
-        tmem_ld32(taddr + 32, v);                  // columns 32..63 (32..48 used)
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
-        if (r == 0) TRACE(it, 6);
+        for (int c4 = 0; c4 < 4; ++c4) {           // 16 accumulator columns at a time keeps the register peak low
+          float v[16], w[16];
+          tmem_ld16(taddr + 16 * c4, v);           // (A_hi + A_lo) S_hi ...
+          tmem_ld16(taddr + 64 + 16 * c4, w);      // ... + A_hi S_lo
+          if (c4 == 3) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
+            if (r == 0) TRACE(it, 6);
+          }
 #pragma unroll
-        for (int k = 32; k < H_A; ++k) {
-          h[k] = 0.f;
-          if (k < kP) {
-            const float v0 = __shfl_sync(0xffffffffu, v[k - 32], src0), v1 = __shfl_sync(0xffffffffu, v[k - 32], src1);
-            h[k] = ux * v0 + wx * v1;
+          for (int j = 0; j < 16; ++j) {
+            const int k = 16 * c4 + j;
+            if (k < kP) {
+              const float c = v[j] + w[j];
+              const float v0 = __shfl_sync(0xffffffffu, c, src0), v1 = __shfl_sync(0xffffffffu, c, src1);
+              h[k] = ux * v0 + wx * v1;
+            } else if (k < H_A) {
+              h[k] = 0.f;
+            }
           }
         }
         bool own;
