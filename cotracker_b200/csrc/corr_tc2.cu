@@ -50,17 +50,19 @@ constexpr int H_FRAME = 8 * H_ROW;        // floats: x-blended correlations [row
 constexpr int H_GROUP = 2 * H_FRAME * 4;  // bytes per epilogue group (2 frames)
 constexpr int ROW_BYTES = 2 * kVolPad * 2;   // 9728: one volume row image [hi | lo]
 static_assert(2 * ROW_BYTES <= H_GROUP, "the output image of a tile reuses the blend buffer");
+constexpr int NACC = 4;                   // TMEM accumulators (tile it -> it % NACC): the MMA issuer runs ahead of the epilogue
+constexpr uint32_t TMEM_COLS = NACC * 128;  // each: 64 columns (A_hi+A_lo) S_hi | 64 columns A_hi S_lo
+constexpr int NPARAM = 8;                 // parameter ring: a tile's slot may only be rewritten after its epilogue read it
 constexpr int OFF_A = 0;
 constexpr int OFF_S = OFF_A + NSLOT * A_SLOT;
 constexpr int OFF_H = OFF_S + S_BYTES;
 constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*H_ROW, row1*H_ROW, -}
 constexpr int XCH_GROUP = 2 * 7 * H_A * 4;       // texel row 4 of both frames: [frame][a][k], register y-blend path
 constexpr int OFF_XCH = OFF_TAB + 2 * 2 * 8 * 16;
-constexpr int OFF_PARAM = OFF_XCH + 2 * XCH_GROUP;   // [slot 4][frame 2] x {cx, cy, box_x, box_y}
-constexpr int OFF_BAR = OFF_PARAM + 4 * 2 * 16;
+constexpr int OFF_PARAM = OFF_XCH + 2 * XCH_GROUP;   // [slot NPARAM][frame 2] x {cx, cy, box_x, box_y}
+constexpr int OFF_BAR = OFF_PARAM + NPARAM * 2 * 16;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-constexpr uint32_t TMEM_COLS = 256;       // 2 accumulators x (64 columns A*S_hi | 64 columns A_hi*S_lo)
 
 struct Corr2Args {
   PyramidLayout lay;
@@ -106,11 +108,11 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* a_full = bars;                  // [NSLOT] TMA -> MMA         (count 1 + tx bytes)
   uint64_t* a_empty = bars + NSLOT;         // [NSLOT] MMA -> TMA         (tcgen05.commit)
-  uint64_t* d_full = bars + 2 * NSLOT;      // [2] MMA -> epilogue group  (tcgen05.commit)
-  uint64_t* d_empty = bars + 2 * NSLOT + 2; // [2] epilogue group -> MMA  (count 4)
-  uint64_t* s_full = bars + 2 * NSLOT + 4;  // builders -> MMA, per unit  (count 2)
-  uint64_t* s_empty = bars + 2 * NSLOT + 5; // MMA -> builders, per unit  (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 6);
+  uint64_t* d_full = bars + 2 * NSLOT;             // [NACC] MMA -> epilogue group  (tcgen05.commit)
+  uint64_t* d_empty = bars + 2 * NSLOT + NACC;     // [NACC] epilogue group -> MMA  (count 4)
+  uint64_t* s_full = bars + 2 * NSLOT + 2 * NACC;      // builders -> MMA, per unit  (count 2)
+  uint64_t* s_empty = bars + 2 * NSLOT + 2 * NACC + 1; // MMA -> builders, per unit  (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * NACC + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_unit = (g.T + 1) / 2;
@@ -123,7 +125,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 4);
     }
@@ -165,7 +167,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
               mbar_wait_spin(&a_empty[sl], ((hc / NSLOT) & 1u) ^ 1u);
               if (kh == 0) TRACE(it, 1);
               if (kh == 0) {   // the tile's parameters become visible to the epilogue through a_full -> d_full
-                float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it & 3) * 32);
+                float4* prm = reinterpret_cast<float4*>(smem + OFF_PARAM + (it % NPARAM) * 32);
                 prm[0] = make_float4(cx0, cy0, __int_as_float(bx0), __int_as_float(by0));
                 prm[1] = make_float4(cx1, cy1, __int_as_float(bx1), __int_as_float(by1));
               }
@@ -196,14 +198,14 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
       for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
         mbar_wait_spin(s_full, ui & 1u);
         for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
-          const int acc = it & 1;
+          const int acc = it % NACC;
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
 #pragma unroll
           for (int kh = 0; kh < 2; ++kh, ++hc) {
             const int sl = hc % NSLOT;
             mbar_wait_spin(&a_full[sl], (hc / NSLOT) & 1u);
             if (kh == 0) TRACE(it, 2);
-            if (kh == 0) mbar_wait_spin(&d_empty[acc], ((it >> 1) & 1u) ^ 1u);
+            if (kh == 0) mbar_wait_spin(&d_empty[acc], ((it / NACC) & 1u) ^ 1u);
             if (kh == 0) TRACE(it, 3);
             tc_fence_after_sync();
             const uint32_t a_base = smem_u32(smem + OFF_A + sl * A_SLOT);
@@ -270,7 +272,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
     float4* tab = reinterpret_cast<float4*>(smem + OFF_TAB + grp * 256);
     float4* xch = reinterpret_cast<float4*>(smem + OFF_XCH + grp * XCH_GROUP);
     float4* hrow = reinterpret_cast<float4*>(hbuf + f * H_FRAME + py * H_ROW + a * H_A);
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int bar_id = 1 + grp;
     // volume row owned by this thread when the y-blend runs ...
     //   in registers (interior tiles): lane (texel row b = py < 7, a = px < 7) of frame f -> rho = a*7 + b
@@ -288,10 +290,12 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
       const int H = g.lay.h[l], W = g.lay.w[l];
       for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
         if ((int)(it & 1u) != grp) continue;
-        mbar_wait(&d_full[grp], (it >> 1) & 1u);
+        const int acc = it % NACC;
+        const uint32_t taddr = tlane + (uint32_t)(acc * 128);
+        mbar_wait(&d_full[acc], (it / NACC) & 1u);
         if (r == 0) TRACE(it, 5);
         tc_fence_after_sync();
-        const float4* prms = reinterpret_cast<const float4*>(smem + OFF_PARAM + (it & 3) * 32);
+        const float4* prms = reinterpret_cast<const float4*>(smem + OFF_PARAM + (it % NPARAM) * 32);
         const float4 prm = prms[f];
         int sx0, sx1;
         float wx;
@@ -312,28 +316,25 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         const float wy = __shfl_sync(0xffffffffu, wy_l, f * 8 + min(py, 6));   // this lane's row weight (fast path)
         // ---- x-blend: h[k] = (1-wx) D[(row, x0), k] + wx D[(row, x1), k]  for (texel row py, sample column a)
         float h[H_A];
+        // drain the accumulator first (h[k] = (A_hi + A_lo) S_hi + A_hi S_lo, 16 columns at a time) and hand it back to
+        // the MMA issuer before any blending: TMEM is the resource the next-but-one tile waits for
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {           // 16 accumulator columns at a time keeps the register peak low
+        for (int c4 = 0; c4 < 4; ++c4) {
           float v[16], w[16];
-          tmem_ld16(taddr + 16 * c4, v);           // (A_hi + A_lo) S_hi ...
-          tmem_ld16(taddr + 64 + 16 * c4, w);      // ... + A_hi S_lo
-          if (c4 == 3) {
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[grp]);  // accumulator drained (registers hold the rest)
-            if (r == 0) TRACE(it, 6);
-          }
+          tmem_ld16(taddr + 16 * c4, v);
+          tmem_ld16(taddr + 64 + 16 * c4, w);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int k = 16 * c4 + j;
-            if (k < kP) {
-              const float c = v[j] + w[j];
-              const float v0 = __shfl_sync(0xffffffffu, c, src0), v1 = __shfl_sync(0xffffffffu, c, src1);
-              h[k] = ux * v0 + wx * v1;
-            } else if (k < H_A) {
-              h[k] = 0.f;
-            }
-          }
+          for (int j = 0; j < 16; ++j)
+            if (16 * c4 + j < H_A) h[16 * c4 + j] = (16 * c4 + j < kP) ? v[j] + w[j] : 0.f;
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[acc]);
+        if (r == 0) TRACE(it, 6);
+#pragma unroll
+        for (int k = 0; k < kP; ++k) {
+          const float v0 = __shfl_sync(0xffffffffu, h[k], src0), v1 = __shfl_sync(0xffffffffu, h[k], src1);
+          h[k] = ux * v0 + wx * v1;
         }
         bool own;
         int ff, rho;
