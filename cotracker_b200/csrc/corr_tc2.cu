@@ -14,19 +14,24 @@
 //   pyramid : a split-bf16 copy [level][plane hi|lo][T][H][W][128] made once per update-loop call
 //   A tile  [128 x 128] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, plane, K-half) is ONE 4-D
 //             TMA box (64 ch x 8 x 8 x 1) landing directly in the 128B-swizzled K-major operand layout; the ring
-//             holds 4 K-half slots (32 KiB: hi|lo x 2 frames), freed as soon as their 12 MMAs retire -- the loop is
-//             bound by TMA latency x bytes in flight, so slot granularity matters more than MMA rate
+//             holds 4 K-half slots (32 KiB: hi|lo x 2 frames), each freed as soon as its 8 MMAs retire
 //   B tile  [128 x 128] : rows 0..63 hi plane / 64..127 lo plane of the 49 support vectors of (n,l) (rows 49..63
 //             of each plane zero), built once per unit by 2 warps
 //   D       [128 x 128] : fp32 in TMEM, 2 tcgen05.mma per k16 step: A_hi x [S_hi ; S_lo] (N=128, A_hi fetched once
-//             for both products) and A_lo x S_hi (N=64); the epilogue adds columns k and 64+k; 2 accumulators
-//   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld -> x-blend by warp shuffles inside each 8-texel
-//             row -> y-blend: interior tiles entirely in registers (next texel row = 8 lanes up, texel row 4 crosses
+//             for both products) and A_lo x S_hi (N=64); the epilogue adds columns k and 64+k; 4 accumulators, so
+//             the MMA issuer runs up to 4 tiles ahead of the epilogue
+//   epilogue (2 groups x 4 warps, alternating tiles): tcgen05.ld (accumulator handed back at once) -> x-blend by
+//             warp shuffles inside each 8-texel row -> y-blend: interior tiles entirely in registers (next texel row = 8 lanes up, texel row 4 crosses
 //             the warp boundary through a 3 KiB exchange buffer); tiles with a border clamp through a shared
 //             [row][a][k] buffer and a per-row tap table -> one thread per volume row ->
 //             split-bf16 byte image of the two 9728-byte volume rows (reusing the blend buffer, K padding zero)
 //             -> one bulk shared->global copy (TMA engine) per 9728-byte volume row
 // Warps: 0 TMA issuer, 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
+// Diagnostics: -DCT3_TRACE records a clock64 timeline of CTA 0 (8 events per tile) and prints it after the 3rd launch.
+// Measured (N=6400, T=16): 1.8-2.0 ms per launch.  Knock-out builds show no single saturated resource: without the
+// epilogue 1.49 ms, with half the TMA bytes or a third of the MMAs -9 % each; the per-warp dependent-instruction
+// latency of the 8 epilogue warps (~800 instructions per tile and warp, 2 such warps per scheduler) is what the
+// producer side ends up waiting for, and registers (168 x 384 threads = the whole file) cap the warp count.
 #include <cstdio>
 #include "gemm.cuh"
 #include "kernels.cuh"
