@@ -38,6 +38,17 @@ def test_abi_argument_validation_without_gpu():
     assert lib.ct3_set_option(b"nope", 1) == -1
     assert engine.get_option("gemm") == 0
     assert lib.ct3_update_loop(None, None, 1, 1, None, None, None, None, None, None, 1, 1, 1, None, 0, None) == -1
+    # the split-bf16 pyramid copy of the correlation kernel is part of the workspace iff every level is >= 8x8 texels
+    *_, total = engine.pyramid_layout(16, 96, 128)
+    assert engine.workspace_bytes(16, 6400, 96, 128) - engine.workspace_bytes(16, 6400) == total * 4
+    assert engine.workspace_bytes(4, 10, 24, 32) == engine.workspace_bytes(4, 10)       # level 3 is 3x4
+    assert lib.ct3_workspace_bytes(4, 10, 4, 4, ctypes.byref(n)) == -1                    # level 3 would be 0x0
+    # stage entry: argument checks come before any launch
+    one = ctypes.c_void_p(256)
+    assert lib.ct3_corr_sample(None, 96, 128, one, None, one, 2, 5, one, None, 0, None) == -1
+    assert lib.ct3_corr_sample(one, 96, 128, one, None, one, 2, 5, one, ctypes.c_void_p(264), 1 << 30, None) == -1
+    assert b"256-byte aligned" in lib.ct3_last_error()
+    assert lib.ct3_corr_sample(one, 96, 128, one, None, one, 2, 5, one, ctypes.c_void_p(512), 1024, None) == -3   # CT3_ENOSPC
 
 
 def test_weight_names_match_state_dict():
