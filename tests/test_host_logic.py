@@ -132,3 +132,32 @@ def test_replica_sharding_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "OK 0 [0, 2, 4]" in r.stdout and "OK 1 [1, 3]" in r.stdout
+
+
+def test_corr_patch_taps_stay_in_box():
+    """fp32 restatement of box_origin8 / tap_pair (csrc/corr_tc2.cu): for every map size >= 8 and every coordinate --
+    far outside, on texel centres, one ulp either side of them -- both bilinear taps of all 7 border-clamped samples
+    lie inside the 8-texel box the TMA load fetches, once a zero-weight second tap is folded onto the first (the case
+    `c + offset` rounding up to an integer in fp32).  The kernel relies on this to index the box without a fallback."""
+    import numpy as np
+    f32 = np.float32
+    rng = np.random.default_rng(0)
+    for size in (8, 9, 12, 16, 24, 48, 96, 128, 1000):
+        ints = np.arange(-6, size + 7).astype(f32)
+        near = [ints]
+        lo, hi = ints.copy(), ints.copy()
+        for _ in range(6):
+            lo, hi = np.nextafter(lo, f32(-1e9)), np.nextafter(hi, f32(1e9))
+            near += [lo.copy(), hi.copy()]
+        c = np.concatenate([rng.uniform(-40, size + 40, 100000).astype(f32), np.array([-1e9, 1e9], dtype=f32)] + near)
+        cc = np.minimum(np.maximum(c, f32(-16)), f32(size + 16)).astype(f32)
+        origin = np.clip(np.floor(cc).astype(np.int64) - 3, 0, size - 8)
+        for a in range(7):
+            x = np.minimum(np.maximum((c + f32(a - 3)).astype(f32), f32(0)), f32(size - 1)).astype(f32)
+            xf = np.floor(x)
+            x0 = xf.astype(np.int64)
+            w = (x - xf).astype(f32)
+            x1 = np.minimum(x0 + 1, size - 1)
+            s0 = x0 - origin
+            s1 = np.where(w > 0, x1 - origin, s0)
+            assert s0.min() >= 0 and s0.max() <= 7 and s1.min() >= 0 and s1.max() <= 7, (size, a)
