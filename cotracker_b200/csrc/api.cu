@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -15,9 +16,25 @@ using namespace ct3;
 namespace {
 
 thread_local char g_err[512] = "";
-int g_opt_gemm = 0;  // 0 tcgen05, 1 SIMT verification
-int g_opt_corr = 0;  // 0 tcgen05 fused kernel, 1 SIMT verification
-int g_opt_attn = 0;  // 0 tensor-core flash kernel, 1 SIMT verification
+// Options and the profiler are PER HOST THREAD (thread_local): a thread that drives its own GPU/stream never sees
+// another thread's verification switches or profile records.
+struct OptDef { const char* name; int lo, hi; };
+enum { OPT_GEMM = 0, OPT_CORR, OPT_ATTN, OPT_PREC_CORR, OPT_PREC_FC1, OPT_COUNT };
+constexpr int kDefPrecCorr = 3, kDefPrecFc1 = 3;
+constexpr OptDef kOptDefs[OPT_COUNT] = {
+    {"gemm", 0, 1},   // 0 tcgen05, 1 SIMT verification
+    {"corr", 0, 2},   // 0 tcgen05 correlate-then-interpolate (corr_tc2.cu), 1 exact-fp32 SIMT, 2 corr_tc.cu
+    {"attn", 0, 1},   // 0 tensor-core kernels, 1 exact-fp32 SIMT verification
+    // tensor-core products per FLOP of a GEMM group: 3 = split x split (hi*hi + lo*hi + hi*lo),
+    // 2 = fp16 activation plane x split fp16 weights, 1 = single fp16 product.  Only the correlation branch has the
+    // switch: SURVEY 7.3 measured that every transformer GEMM breaks the 1e-3 px budget with fewer than 3 products.
+    {"prec.corr", 1, 3},   // the 49x128x49 correlation contraction (corr_tc2.cu)
+    {"prec.fc1", 1, 3},    // corr_mlp.fc1 (K = 2401): 1|2 also make the correlation volume a single fp16 plane
+};
+thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1};
+#define g_opt_gemm g_opt[OPT_GEMM]
+#define g_opt_corr g_opt[OPT_CORR]
+#define g_opt_attn g_opt[OPT_ATTN]
 
 int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -33,13 +50,17 @@ int fail_cuda(cudaError_t e, const char* where) {
     if (e__ != cudaSuccess) return fail_cuda(e__, where); \
   } while (0)
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      n = 148;
+int num_sms() {   // of the CURRENT device (one process may drive several GPUs)
+  static std::atomic<int> cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
   }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 
@@ -48,8 +69,8 @@ int num_sms() {
 // optional live profiler: CUDA events around every launch, summed per kernel category (bench.py roofline)
 enum { CAT_CORR = 0, CAT_GEMM = 1, CAT_ATTN = 2, CAT_LN = 3, CAT_MISC = 4, CAT_COUNT = 5 };
 struct ProfRec { int cat; cudaEvent_t a, b; double flops; };
-bool g_prof_on = false;
-std::vector<ProfRec> g_prof;
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof;
 struct ProfScope {
   cudaStream_t s; int cat; double flops; cudaEvent_t a = nullptr, b = nullptr;
   ProfScope(cudaStream_t s_, int cat_, double flops_ = 0.0) : s(s_), cat(cat_), flops(flops_) {
@@ -77,6 +98,7 @@ struct Block {
 };
 struct Layout {
   Lin corr_fc1, corr_fc2, in_tr;
+  Lin corr_fc1_h;   // corr_mlp.fc1 once more as split fp16 planes (prec.fc1 = 1 | 2); shares corr_fc1's bias
   Block time[kDepth], vself[kDepth], p2v[kDepth], v2p[kDepth];
   size_t heads_w = 0, heads_b = 0, virt = 0, win_f32 = 0;
   size_t total = 0;
@@ -108,11 +130,11 @@ void place_block(Block& b, bool cross, size_t& off) {
   place_lin(b.fc2, kC, kMlpHid, off);
 }
 const Layout& layout() {
-  static Layout L;
-  static bool init = false;
-  if (!init) {
+  static const Layout L0 = [] {   // C++11 thread-safe one-time initialisation
+    Layout L;
     size_t off = 0;
     place_lin(L.corr_fc1, kCorrHid, kVol, off);
+    place_lin(L.corr_fc1_h, kCorrHid, kVol, off);
     place_lin(L.corr_fc2, kCorrOut, kCorrHid, off);
     place_lin(L.in_tr, kC, kX, off);
     L.win_f32 = off; off = align_up(off + (size_t)kC * kX * sizeof(float));
@@ -126,16 +148,16 @@ const Layout& layout() {
       place_block(L.v2p[i], true, off);
     }
     L.total = off;
-    init = true;
-  }
-  return L;
+    return L;
+  }();
+  return L0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight tensor order expected by ct3_pack_weights
 const std::vector<std::string>& weight_names() {
-  static std::vector<std::string> names;
-  if (names.empty()) {
+  static const std::vector<std::string> names0 = [] {
+    std::vector<std::string> names;
     const char* head[] = {"corr_mlp.fc1.weight", "corr_mlp.fc1.bias", "corr_mlp.fc2.weight", "corr_mlp.fc2.bias",
                           "updateformer.input_transform.weight", "updateformer.input_transform.bias",
                           "updateformer.virual_tracks", "updateformer.flow_head.weight", "updateformer.flow_head.bias",
@@ -155,8 +177,9 @@ const std::vector<std::string>& weight_names() {
       for (const char* t : cross_t) names.push_back("updateformer.space_point2virtual_blocks." + idx + t);
       for (const char* t : cross_t) names.push_back("updateformer.space_virtual2point_blocks." + idx + t);
     }
-  }
-  return names;
+    return names;
+  }();
+  return names0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -208,8 +231,12 @@ struct Runner {
   int impl;
   const char* gerr = nullptr;
 
-  int gemm(const __nv_bfloat16* x, const Lin& lin, int M, const GemmEpilogue& e) {
+  int gemm(const __nv_bfloat16* x, const Lin& lin, int M, const GemmEpilogue& e, int products = 3, int fp16 = 0,
+           int64_t x_ld = 0) {
     GemmProblem p;
+    p.products = products;
+    p.fp16 = fp16;
+    p.x_ld = x_ld;
     p.x_split = x;
     p.w_split = reinterpret_cast<const __nv_bfloat16*>(pk + lin.w);
     p.M = M;
@@ -344,6 +371,17 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
   return 0;
 }
 
+// effective precision of the correlation branch for this thread's options: the single-plane / fewer-product modes
+// exist in corr_tc2.cu only, so whenever another correlation kernel runs the branch computes split x split
+struct Prec { int corr, fc1; bool patch; bool vol16() const { return fc1 < 3; } };
+Prec effective_prec(bool have_pyr_split, int T, int H4, int W4) {
+  Prec p;
+  p.patch = corr_uses_patch_kernel(g_opt_corr, have_pyr_split, T, H4, W4);
+  p.corr = p.patch ? g_opt[OPT_PREC_CORR] : 3;
+  p.fc1 = p.patch ? g_opt[OPT_PREC_FC1] : 3;
+  return p;
+}
+
 int check_TN(int T, int N) {
   if (T < 1 || N < 1) return fail(CT3_EINVAL, "T and N must be >= 1%s");
   if ((int64_t)(N + kV) * T * 3 * kC >= (int64_t)1 << 40) return fail(CT3_EINVAL, "problem too large%s");
@@ -360,17 +398,28 @@ const char* ct3_last_error(void) { return g_err; }
 
 int ct3_set_option(const char* name, int value) {
   if (!name) return fail(CT3_EINVAL, "null option name%s");
-  if (!strcmp(name, "gemm")) { if (value < 0 || value > 1) return fail(CT3_EINVAL, "gemm option must be 0 or 1%s"); g_opt_gemm = value; return 0; }
-  if (!strcmp(name, "corr")) { g_opt_corr = value; return 0; }
-  if (!strcmp(name, "attn")) { g_opt_attn = value; return 0; }
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (!strcmp(name, kOptDefs[i].name)) {
+      if (value < kOptDefs[i].lo || value > kOptDefs[i].hi) return fail(CT3_EINVAL, "option value out of range: %s", name);
+      g_opt[i] = value;
+      return 0;
+    }
   return fail(CT3_EINVAL, "unknown option %s", name);
 }
 int ct3_get_option(const char* name, int* value) {
   if (!name || !value) return fail(CT3_EINVAL, "null argument%s");
-  if (!strcmp(name, "gemm")) { *value = g_opt_gemm; return 0; }
-  if (!strcmp(name, "corr")) { *value = g_opt_corr; return 0; }
-  if (!strcmp(name, "attn")) { *value = g_opt_attn; return 0; }
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (!strcmp(name, kOptDefs[i].name)) { *value = g_opt[i]; return 0; }
   return fail(CT3_EINVAL, "unknown option %s", name);
+}
+
+int ct3_precision_info(int T, int H4, int W4, int* corr_products, int* fc1_products, int* volume_bytes_per_element) {
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  const Prec pr = effective_prec(true, T, H4, W4);
+  if (corr_products) *corr_products = pr.corr;
+  if (fc1_products) *fc1_products = pr.fc1;
+  if (volume_bytes_per_element) *volume_bytes_per_element = pr.vol16() ? 2 : 4;
+  return 0;
 }
 
 int ct3_num_weight_tensors(void) { return (int)weight_names().size(); }
@@ -396,8 +445,9 @@ int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t 
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
   CK(cudaMemsetAsync(pk, 0, L.total, s), "memset packed");
-  auto put_lin = [&](const Lin& l, const float* w, const float* b, int rows, int row_off, int perm) -> cudaError_t {
-    cudaError_t e = launch_split_rows(w, rows, l.K, l.Kpad, perm, reinterpret_cast<__nv_bfloat16*>(pk + l.w), row_off, s);
+  auto put_lin = [&](const Lin& l, const float* w, const float* b, int rows, int row_off, int perm,
+                     int fp16 = 0) -> cudaError_t {
+    cudaError_t e = launch_split_rows(w, rows, l.K, l.Kpad, perm, reinterpret_cast<__nv_bfloat16*>(pk + l.w), row_off, s, fp16);
     if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(pk + l.b + (size_t)row_off * 4, b, (size_t)rows * 4, cudaMemcpyDeviceToDevice, s);
   };
@@ -405,7 +455,8 @@ int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t 
     return cudaMemcpyAsync(pk + off, src, count * 4, cudaMemcpyDeviceToDevice, s);
   };
   int k = 0;
-  CK(put_lin(L.corr_fc1, t[k], t[k + 1], kCorrHid, 0, 0), "pack corr_fc1"); k += 2;
+  CK(put_lin(L.corr_fc1, t[k], t[k + 1], kCorrHid, 0, 0), "pack corr_fc1");
+  CK(put_lin(L.corr_fc1_h, t[k], t[k + 1], kCorrHid, 0, 0, /*fp16*/ 1), "pack corr_fc1 (fp16 planes)"); k += 2;
   CK(put_lin(L.corr_fc2, t[k], t[k + 1], kCorrOut, 0, 0), "pack corr_fc2"); k += 2;
   CK(put_lin(L.in_tr, t[k], t[k + 1], kC, 0, /*perm_x*/ 1), "pack input_transform");
   CK(put_f32(L.win_f32, t[k], (size_t)kC * kX), "pack input_transform fp32"); k += 2;
@@ -515,14 +566,15 @@ int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support, cons
   if (int rc = check_TN(T, N)) return rc;
   if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
   const __nv_bfloat16* pyr_split = nullptr;
-  if (scratch && g_opt_corr == 0 && corr_patch_supported(T, H4, W4)) {
+  const Prec pr = effective_prec(scratch != nullptr, T, H4, W4);
+  if (pr.patch) {
     if ((uintptr_t)scratch & 255) return fail(CT3_EINVAL, "scratch must be 256-byte aligned%s");
     if (scratch_bytes < (size_t)pyramid_layout(T, H4, W4).total * 4) return fail(CT3_ENOSPC, "scratch too small%s");
-    CK(launch_split_pyramid(pyr, T, H4, W4, (__nv_bfloat16*)scratch, (cudaStream_t)stream), "split_pyramid");
+    CK(launch_split_pyramid(pyr, T, H4, W4, (__nv_bfloat16*)scratch, pr.corr, (cudaStream_t)stream), "split_pyramid");
     pyr_split = (const __nv_bfloat16*)scratch;
   }
   CK(launch_corr_sample(pyr, pyr_split, H4, W4, support, track_valid, coords, T, N, (__nv_bfloat16*)vol_split,
-                        g_opt_corr, num_sms(), (cudaStream_t)stream), "corr_sample");
+                        g_opt_corr, pr.corr, pr.vol16() ? 1 : 0, num_sms(), (cudaStream_t)stream), "corr_sample");
   return 0;
 }
 
@@ -532,12 +584,27 @@ int ct3_split_rows(const float* x, int rows, int K, int Kpad, void* x_split, ct3
   return 0;
 }
 
+int ct3_split_rows_fp16(const float* x, int rows, int K, int Kpad, void* x_split, ct3_stream_t stream) {
+  if (!x || !x_split || rows < 1 || K < 1 || Kpad < K || (Kpad % 64)) return fail(CT3_EINVAL, "bad split_rows argument%s");
+  CK(launch_split_rows(x, rows, K, Kpad, 0, (__nv_bfloat16*)x_split, 0, (cudaStream_t)stream, /*fp16*/ 1), "split_rows");
+  return 0;
+}
+
 int ct3_linear(const void* x_split, const void* w_split, const float* bias, int M, int Nout, int Kpad, int act,
                float* y, ct3_stream_t stream) {
+  return ct3_linear_prec(x_split, w_split, bias, M, Nout, Kpad, act, 3, 0, y, stream);
+}
+
+int ct3_linear_prec(const void* x_split, const void* w_split, const float* bias, int M, int Nout, int Kpad, int act,
+                    int products, int fp16, float* y, ct3_stream_t stream) {
   if (!x_split || !w_split || !y) return fail(CT3_EINVAL, "null argument%s");
   if (M < 1 || Nout < 1 || (Nout % 128) || Kpad < 64 || (Kpad % 64) || act < 0 || act > 2)
     return fail(CT3_EINVAL, "ct3_linear: need M>=1, Nout %% 128 == 0, Kpad %% 64 == 0, act in 0..2%s");
+  if (products < 1 || products > 3 || fp16 < 0 || fp16 > 1)
+    return fail(CT3_EINVAL, "ct3_linear_prec: products in 1..3, fp16 in 0..1%s");
   GemmProblem p;
+  p.products = products;
+  p.fp16 = fp16;
   p.x_split = (const __nv_bfloat16*)x_split;
   p.w_split = (const __nv_bfloat16*)w_split;
   p.M = M; p.N = Nout; p.Kpad = Kpad;
@@ -570,8 +637,9 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
   const uint8_t* pk = R.pk;
   const int Rp = N * T, Mc = Rp * kL;
   // split-bf16 copy of the window's pyramid: the TMA source of the correlation kernel, made once per call
-  const __nv_bfloat16* pyr_split = (g_opt_corr == 0 && iters > 0) ? W.pyr_split : nullptr;
-  if (pyr_split) RUNC(CAT_MISC, launch_split_pyramid(pyr, T, H4, W4, W.pyr_split, R.s));
+  const Prec pr = effective_prec(W.pyr_split != nullptr, T, H4, W4);
+  const __nv_bfloat16* pyr_split = (pr.patch && iters > 0) ? W.pyr_split : nullptr;
+  if (pyr_split) RUNC(CAT_MISC, launch_split_pyramid(pyr, T, H4, W4, W.pyr_split, pr.corr, R.s));
 
   // W_in * time_emb[t]: x + time_emb is folded into a per-frame bias of input_transform (cotracker3_offline.py:196)
   RUNC(CAT_MISC, launch_row_bias(time_emb, reinterpret_cast<const float*>(pk + L.win_f32), T, W.row_bias, R.s));
@@ -579,9 +647,15 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
   for (int it = 0; it < iters; ++it) {
     // (i)+(ii) sampling + 4-D correlation, all levels -> split volume
     RUNC(CAT_CORR, launch_corr_sample(pyr, pyr_split, H4, W4, support, track_valid, coords, T, N, W.vol, g_opt_corr,
-                                      num_sms(), R.s));
+                                      pr.corr, pr.vol16() ? 1 : 0, num_sms(), R.s));
     // (iii) corr_mlp: 2401 -> 384 (GELU erf) -> 256, written straight into X columns [256*l, 256*l+256)
-    RUNC(-1, R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
+    if (pr.vol16()) {   // single fp16 volume plane x split fp16 weights: 2 (or 1) tensor-core products per FLOP
+      GemmEpilogue e1 = Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1);
+      e1.bias = reinterpret_cast<const float*>(pk + L.corr_fc1.b);
+      RUNC(-1, R.gemm(W.vol, L.corr_fc1_h, Mc, e1, pr.fc1, /*fp16*/ 1, kVolPad));
+    } else {
+      RUNC(-1, R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
+    }
     {
       GemmEpilogue e = Runner::to_split(W.xs, 2 * kXPad, kXPad, 0);
       e.row_group = kL;
@@ -630,16 +704,15 @@ namespace {
 constexpr int kEncCin = 416, kEncMid = 256, kEncK = kEncCin * 9;
 struct EncLayout { Lin conv2, conv3; size_t total; };
 const EncLayout& enc_layout() {
-  static EncLayout E;
-  static bool init = false;
-  if (!init) {
+  static const EncLayout E0 = [] {
+    EncLayout E;
     size_t off = 0;
     place_lin(E.conv2, kEncMid, kEncK, off);
     place_lin(E.conv3, kD, kEncMid, off);
     E.total = off;
-    init = true;
-  }
-  return E;
+    return E;
+  }();
+  return E0;
 }
 struct EncWs { __nv_bfloat16* a; float* y; __nv_bfloat16* ys; float* stats; size_t total; int tc; };
 EncWs enc_carve(void* base, int T, int H4, int W4) {

@@ -299,11 +299,12 @@ cudaError_t launch_variant(const AttnParams& p, int num_splits, int qtw, float* 
   constexpr int SLICE_BYTES = (2 * KB * KPAD + 2 * kDh * VPAD) * 2;
   const int smem = SLICE_BYTES * (PER_WARP ? WARPS : 1);
   const int q_tiles = (p.Lq + 15) / 16;
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<KB, PER_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static DeviceOnce attr;
+  if (smem > 48 * 1024) {
+    cudaError_t e = once_per_device(attr, [&] {
+      return cudaFuncSetAttribute(attention_tc_kernel<KB, PER_WARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   if (PER_WARP) {
     const long long items = (long long)p.num_seq * kHeads * q_tiles;

@@ -4,10 +4,31 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace ct3 {
+
+// ----------------------------------------------------------------------------------------------
+// Function attributes (max dynamic shared memory) are PER DEVICE: one process may drive several GPUs, from several
+// host threads.  `once_per_device(flag, f)` runs f() the first time it is reached on the current device (a benign
+// race may run it twice; cudaFuncSetAttribute is idempotent).
+struct DeviceOnce { std::atomic<uint64_t> done[2] = {}; };   // up to 128 devices
+template <typename F>
+inline cudaError_t once_per_device(DeviceOnce& flag, F&& f) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 128) return f();
+  const uint64_t bit = 1ull << (dev & 63);
+  if (flag.done[dev >> 6].load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = f();
+  if (e == cudaSuccess) flag.done[dev >> 6].fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 // ----------------------------------------------------------------------------------------------
 // model constants (mirrors include/ct3_b200.h)
@@ -61,6 +82,21 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// fp16 flavour of the same split (hi = fp16(x), lo = fp16(x - hi)): |x - hi - lo| <= 2^-22 |x| for normal lo;
+// used only where the values are known to sit well inside fp16's range (unit-norm features, correlations in [-1,1],
+// the correlation-MLP weights)
+__device__ __forceinline__ void split2_h(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {   // nn.GELU() (blocks.py:48)
@@ -261,6 +297,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 //  | N>>3 [17,23) | M>>4 [24,29))
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with A = B = IEEE fp16 (format code 0) when `fp16`, else bf16 (format code 1)
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, bool fp16) {
+  return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // single thread: D[tmem] (+)= A[smem] * B[smem]^T
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

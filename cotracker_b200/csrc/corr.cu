@@ -121,11 +121,16 @@ corr_sample_simt_kernel(CorrArgs g) {
 
 }  // namespace
 
+bool corr_uses_patch_kernel(int impl, bool have_pyr_split, int T, int H4, int W4) {
+  return impl == 0 && have_pyr_split && corr_patch_supported(T, H4, W4);
+}
+
 cudaError_t launch_corr_sample(const float* pyr, const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                const uint8_t* track_valid, const float* coords, int T, int N,
-                               __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s) {
-  if (impl == 0 && pyr_split != nullptr && corr_patch_supported(T, H4, W4))
-    return launch_corr_patch_tc(pyr_split, H4, W4, support, track_valid, coords, T, N, vol_split, num_sms, s);
+                               __nv_bfloat16* vol_split, int impl, int mode, int vol16, int num_sms, cudaStream_t s) {
+  if (corr_uses_patch_kernel(impl, pyr_split != nullptr, T, H4, W4))
+    return launch_corr_patch_tc(pyr_split, H4, W4, support, track_valid, coords, T, N, vol_split, mode, vol16, num_sms, s);
+  if (vol16) return cudaErrorInvalidValue;   // only the patch kernel writes the single-plane volume
   if (impl != 1) return launch_corr_sample_tc(pyr, H4, W4, support, track_valid, coords, T, N, vol_split, num_sms, s);
   CorrArgs g;  // impl 1: exact-fp32 SIMT verification kernel
   g.pyr = pyr;
@@ -137,11 +142,12 @@ cudaError_t launch_corr_sample(const float* pyr, const __nv_bfloat16* pyr_split,
   g.N = N;
   g.vol = vol_split;
   const int smem = 2 * 52 * kLd * (int)sizeof(float);  // 54.9 KB
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(corr_sample_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static DeviceOnce attr;
+  {
+    cudaError_t e = once_per_device(attr, [&] {
+      return cudaFuncSetAttribute(corr_sample_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   dim3 grid(N, kL);
   corr_sample_simt_kernel<<<grid, 256, smem, s>>>(g);

@@ -411,11 +411,12 @@ cudaError_t launch_corr_sample_tc(const float* pyr, int H4, int W4, const float*
                            CU_TENSOR_MAP_SWIZZLE_NONE))
       return cudaErrorInvalidValue;
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(corr_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  static DeviceOnce attr;
+  {
+    cudaError_t e = once_per_device(attr, [&] {
+      return cudaFuncSetAttribute(corr_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    });
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   const int num_units = N * kL;
   const int grid = num_units < num_sms ? num_units : num_sms;

@@ -44,22 +44,33 @@ constexpr int MMA_WARP = 1;
 constexpr int SB_WARP0 = 2;               // 2 support-builder warps
 constexpr int EPI_WARP0 = 4;              // warps 4..7 group 0, 8..11 group 1; (warp & 3) = TMEM lane quarter
 constexpr int THREADS = 12 * 32;
-constexpr int NSLOT = 4;                  // A ring: slots of one K-half (64 channels) of a 2-frame tile
-constexpr int A_PLANE = 16384;            // one bf16 plane of a slot: [128 rows x 128 B]
-constexpr int A_SLOT = 2 * A_PLANE;       // hi + lo = 32 KiB
+// Precision modes (products per correlation FLOP):
+//   MODE 3: texels split bf16 hi|lo, support split bf16: A_hi x [S_hi;S_lo] + A_lo x S_hi      (rel. err ~2^-17)
+//   MODE 2: texels ONE fp16 plane (rounded, 2^-12), support split fp16: A x [S_hi;S_lo] as one N=128 MMA
+//   MODE 1: texels one fp16 plane, support one fp16 plane: A x S_hi (N=64)
+// MODE <= 2 halves the bytes every tile pulls through the L2->SM path (the resource this kernel saturates:
+// 64 KiB per 2-frame tile in MODE 3) and doubles the tiles in flight for the same 128 KiB ring.
+constexpr int A_PLANE = 16384;            // one 16-bit plane of a slot: [128 rows x 128 B]
+constexpr int A_RING = 131072;            // ring bytes: 4 slots of hi|lo (MODE 3) or 8 single-plane slots
+template <int MODE> struct Ring {
+  static constexpr int A_SLOT = MODE == 3 ? 2 * A_PLANE : A_PLANE;   // one K-half (64 channels) of a 2-frame tile
+  static constexpr int NSLOT = A_RING / A_SLOT;
+};
+constexpr int MAX_NSLOT = 8;
 constexpr int S_HALF = 2 * 8192;          // one K-half of S: [hi rows 0..63 | lo rows 64..127] x 128 B = one N=128 operand
 constexpr int S_BYTES = 2 * S_HALF;       // 32 KiB
 constexpr int H_A = 52;                   // floats per (texel row, a): 49 + pad, keeps every vector 16-byte aligned
 constexpr int H_ROW = 7 * H_A;            // floats per texel row
 constexpr int H_FRAME = 8 * H_ROW;        // floats: x-blended correlations [row 8][a 7][k 52] of one frame
 constexpr int H_GROUP = 2 * H_FRAME * 4;  // bytes per epilogue group (2 frames)
-constexpr int ROW_BYTES = 2 * kVolPad * 2;   // 9728: one volume row image [hi | lo]
-static_assert(2 * ROW_BYTES <= H_GROUP, "the output image of a tile reuses the blend buffer");
+constexpr int ROW_BYTES_SPLIT = 2 * kVolPad * 2;   // 9728: one volume row image [hi | lo] (split bf16)
+constexpr int ROW_BYTES_H16 = kVolPad * 2;         // 4864: one volume row image, single fp16 plane
+static_assert(2 * ROW_BYTES_SPLIT <= H_GROUP, "the output image of a tile reuses the blend buffer");
 constexpr int NACC = 4;                   // TMEM accumulators (tile it -> it % NACC): the MMA issuer runs ahead of the epilogue
 constexpr uint32_t TMEM_COLS = NACC * 128;  // each: 64 columns (A_hi+A_lo) S_hi | 64 columns A_hi S_lo
 constexpr int NPARAM = 8;                 // parameter ring: a tile's slot may only be rewritten after its epilogue read it
 constexpr int OFF_A = 0;
-constexpr int OFF_S = OFF_A + NSLOT * A_SLOT;
+constexpr int OFF_S = OFF_A + A_RING;
 constexpr int OFF_H = OFF_S + S_BYTES;
 constexpr int OFF_TAB = OFF_H + 2 * H_GROUP;     // [group 2][frame 2][b 8] x {wy, row0*H_ROW, row1*H_ROW, -}
 constexpr int XCH_GROUP = 2 * 7 * H_A * 4;       // texel row 4 of both frames: [frame][a][k], register y-blend path
@@ -75,7 +86,7 @@ struct Corr2Args {
   const uint8_t* track_valid;  // [N] or null
   const float* coords;         // [T, N, 2]
   int T, N;
-  __nv_bfloat16* vol;          // [N*T*4, 2*kVolPad]
+  uint16_t* vol;               // [N*T*4, 2*kVolPad] split bf16, or [N*T*4, kVolPad] fp16 (V16)
   long long* trace;            // CT3_TRACE builds: [256 tiles][8 events] clock64 of CTA 0
 };
 #ifdef CT3_TRACE
@@ -84,7 +95,7 @@ struct Corr2Args {
 #define TRACE(tile, ev) do { } while (0)
 #endif
 struct Corr2Maps {
-  CUtensorMap m[kL];           // per level: bf16 dims (128, W, H, 2T), box (64, 8, 8, 1), 128B swizzle
+  CUtensorMap m[kL];           // per level: 16-bit dims (128, W, H, planes*T), box (64, 8, 8, 1), 128B swizzle
 };
 
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
@@ -106,18 +117,22 @@ __device__ __forceinline__ void tap_pair(float c, int off, int size, int origin,
   s1 = (w > 0.f) ? min(max(min(x0 + 1, size - 1) - origin, 0), 7) : s0;
 }
 
+template <int MODE, bool V16>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant__ Corr2Maps maps, int num_units) {
+  constexpr int NSLOT = Ring<MODE>::NSLOT, A_SLOT = Ring<MODE>::A_SLOT;
+  constexpr int ROW_BYTES = V16 ? ROW_BYTES_H16 : ROW_BYTES_SPLIT;
+  constexpr bool F16 = MODE != 3;           // operand planes are IEEE fp16 (else bf16)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* a_full = bars;                  // [NSLOT] TMA -> MMA         (count 1 + tx bytes)
-  uint64_t* a_empty = bars + NSLOT;         // [NSLOT] MMA -> TMA         (tcgen05.commit)
-  uint64_t* d_full = bars + 2 * NSLOT;             // [NACC] MMA -> epilogue group  (tcgen05.commit)
-  uint64_t* d_empty = bars + 2 * NSLOT + NACC;     // [NACC] epilogue group -> MMA  (count 4)
-  uint64_t* s_full = bars + 2 * NSLOT + 2 * NACC;      // builders -> MMA, per unit  (count 2)
-  uint64_t* s_empty = bars + 2 * NSLOT + 2 * NACC + 1; // MMA -> builders, per unit  (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * NACC + 2);
+  uint64_t* a_empty = bars + MAX_NSLOT;     // [NSLOT] MMA -> TMA         (tcgen05.commit)
+  uint64_t* d_full = bars + 2 * MAX_NSLOT;             // [NACC] MMA -> epilogue group  (tcgen05.commit)
+  uint64_t* d_empty = bars + 2 * MAX_NSLOT + NACC;     // [NACC] epilogue group -> MMA  (count 4)
+  uint64_t* s_full = bars + 2 * MAX_NSLOT + 2 * NACC;      // builders -> MMA, per unit  (count 2)
+  uint64_t* s_empty = bars + 2 * MAX_NSLOT + 2 * NACC + 1; // MMA -> builders, per unit  (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_NSLOT + 2 * NACC + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_unit = (g.T + 1) / 2;
@@ -183,7 +198,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
                 if (f < nf) {
                   const int bx = f ? bx1 : bx0, by = f ? by1 : by0;
 #pragma unroll
-                  for (int pl = 0; pl < 2; ++pl)
+                  for (int pl = 0; pl < (MODE == 3 ? 2 : 1); ++pl)
                     tma_load_4d(dst + pl * A_PLANE + f * 8192, &maps.m[l], kh * 64, bx, by, pl * g.T + t0 + k + f,
                                 &a_full[sl]);
                 }
@@ -197,7 +212,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
   } else if (warp == MMA_WARP) {
     // ================================================================== MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64), idesc128 = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc64 = umma_idesc_16(128, 64, F16), idesc128 = umma_idesc_16(128, 128, F16);
       uint32_t it = 0, ui = 0, hc = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);
       for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
@@ -218,10 +233,10 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               // A_hi x [S_hi ; S_lo] as ONE N=128 MMA (A_hi is fetched once for both products): columns 0..63 += A_hi S_hi,
               // columns 64..127 += A_hi S_lo; then A_lo x S_hi (N=64) on columns 0..63.  The epilogue adds the halves.
-              const uint64_t dah = umma_desc_sw128(a_base + j * 32), dal = umma_desc_sw128(a_base + A_PLANE + j * 32);
+              const uint64_t dah = umma_desc_sw128(a_base + j * 32);
               const uint64_t ds = umma_desc_sw128(s_base + (uint32_t)(kh * S_HALF + j * 32));
-              umma_bf16(d_tmem, dah, ds, idesc128, (kh | j) != 0 ? 1u : 0u);
-              umma_bf16(d_tmem, dal, ds, idesc64, 1u);
+              umma_bf16(d_tmem, dah, ds, MODE == 1 ? idesc64 : idesc128, (kh | j) != 0 ? 1u : 0u);
+              if (MODE == 3) umma_bf16(d_tmem, umma_desc_sw128(a_base + A_PLANE + j * 32), ds, idesc64, 1u);
             }
             umma_commit(&a_empty[sl]);   // this K-half may be refilled while the other one is still being multiplied
           }
@@ -254,8 +269,13 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         const int p = sb + 2 * j;
         if (p < kP) {
           uint32_t h0, l0, h1, l1;
-          split2(rows[j].x, rows[j].y, h0, l0);
-          split2(rows[j].z, rows[j].w, h1, l1);
+          if (F16) {
+            split2_h(rows[j].x, rows[j].y, h0, l0);
+            split2_h(rows[j].z, rows[j].w, h1, l1);
+          } else {
+            split2(rows[j].x, rows[j].y, h0, l0);
+            split2(rows[j].z, rows[j].w, h1, l1);
+          }
           const uint32_t off = (uint32_t)(atom * S_HALF) + sw128(p, chunk) + (uint32_t)(half * 8);
           *reinterpret_cast<uint2*>(s_hi + off) = make_uint2(h0, h1);          // rows 0..63 of the K-half: hi plane
           *reinterpret_cast<uint2*>(s_hi + 8192 + off) = make_uint2(l0, l1);   // rows 64..127: lo plane
@@ -325,12 +345,17 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
         // the MMA issuer before any blending: TMEM is the resource the next-but-one tile waits for
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          float v[16], w[16];
+          float v[16];
           tmem_ld16(taddr + 16 * c4, v);
-          tmem_ld16(taddr + 64 + 16 * c4, w);
+          if (MODE >= 2) {
+            float w[16];
+            tmem_ld16(taddr + 64 + 16 * c4, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += w[j];
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (16 * c4 + j < H_A) h[16 * c4 + j] = (16 * c4 + j < kP) ? v[j] + w[j] : 0.f;
+            if (16 * c4 + j < H_A) h[16 * c4 + j] = (16 * c4 + j < kP) ? v[j] : 0.f;
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -401,31 +426,37 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           ff = yf;
           rho = rho_gen;
         }
-        // ---- split-bf16 byte image of the tile's two volume rows ([hi(2432) | lo(2432)] each)
+        // ---- byte image of the tile's two volume rows: [hi(2432) | lo(2432)] split bf16 each, or one fp16 plane (V16)
         if (own) {
-          // 49 bf16 per plane at element offset rho*49: one 2-byte edge element (the first if that offset is odd,
+          // 49 elements per plane at element offset rho*49: one 2-byte edge element (the first if that offset is odd,
           // else the last) + 24 aligned 4-byte pairs
           const bool odd = (rho & 1) != 0;
-          __nv_bfloat16* dst_hi = reinterpret_cast<__nv_bfloat16*>(img + ff * ROW_BYTES) + rho * kP;
-          __nv_bfloat16* dst_lo = dst_hi + kVolPad;
+          uint16_t* dst_hi = reinterpret_cast<uint16_t*>(img + ff * ROW_BYTES) + rho * kP;
           uint32_t* ph = reinterpret_cast<uint32_t*>(dst_hi + (odd ? 1 : 0));
-          uint32_t* pl = reinterpret_cast<uint32_t*>(dst_lo + (odd ? 1 : 0));
+          if (V16) {
 #pragma unroll
-          for (int j = 0; j < 24; ++j) {
-            uint32_t hi, lo;
-            split2(odd ? h[2 * j + 1] : h[2 * j], odd ? h[2 * j + 2] : h[2 * j + 1], hi, lo);
-            ph[j] = hi;
-            pl[j] = lo;
+            for (int j = 0; j < 24; ++j) ph[j] = pack_h2(odd ? h[2 * j + 1] : h[2 * j], odd ? h[2 * j + 2] : h[2 * j + 1]);
+            dst_hi[odd ? 0 : 48] = __half_as_ushort(__float2half_rn(odd ? h[0] : h[48]));
+          } else {
+            uint16_t* dst_lo = dst_hi + kVolPad;
+            uint32_t* pl = reinterpret_cast<uint32_t*>(dst_lo + (odd ? 1 : 0));
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+              uint32_t hi, lo;
+              split2(odd ? h[2 * j + 1] : h[2 * j], odd ? h[2 * j + 2] : h[2 * j + 1], hi, lo);
+              ph[j] = hi;
+              pl[j] = lo;
+            }
+            const bf16pair ed = split_bf16(odd ? h[0] : h[48]);
+            dst_hi[odd ? 0 : 48] = __bfloat16_as_ushort(ed.hi);
+            dst_lo[odd ? 0 : 48] = __bfloat16_as_ushort(ed.lo);
           }
-          const bf16pair ed = split_bf16(odd ? h[0] : h[48]);
-          dst_hi[odd ? 0 : 48] = ed.hi;
-          dst_lo[odd ? 0 : 48] = ed.lo;
         } else {
-          // K padding (elements 2401..2431 of the 4 planes) = zero: one 2-byte element + 15 aligned pairs per plane
-          for (int j = fast ? idle_fast : r - 2 * kP; j < 4 * 16; j += 128 - 2 * kP) {
-            __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(img) + (j >> 4) * kVolPad;
+          // K padding (elements 2401..2431 of every plane of the image) = zero: one 2-byte element + 15 aligned pairs each
+          for (int j = fast ? idle_fast : r - 2 * kP; j < (V16 ? 2 : 4) * 16; j += 128 - 2 * kP) {
+            uint16_t* plane = reinterpret_cast<uint16_t*>(img) + (j >> 4) * kVolPad;
             const int w = j & 15;
-            if (w == 0) plane[kVol] = __float2bfloat16(0.f);
+            if (w == 0) plane[kVol] = 0;
             else *reinterpret_cast<uint32_t*>(plane + kVol - 1 + 2 * w) = 0u;
           }
         }
@@ -438,7 +469,7 @@ corr_patch_tc_kernel(const __grid_constant__ Corr2Args g, const __grid_constant_
           for (int t2 = 0; t2 < 2; ++t2) {
             const int t = 2 * tp + t2;
             if (t < g.T)
-              bulk_store_s2g(g.vol + (((int64_t)n * g.T + t) * kL + l) * (2 * kVolPad), img + t2 * ROW_BYTES, ROW_BYTES);
+              bulk_store_s2g(g.vol + (((int64_t)n * g.T + t) * kL + l) * (ROW_BYTES / 2), img + t2 * ROW_BYTES, ROW_BYTES);
           }
           bulk_commit();
           TRACE(it, 7);
@@ -466,6 +497,27 @@ split_level_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2*
   }
 }
 
+// fp32 channels-last level -> one fp16 plane (MODE 1 / 2), 4 channels per thread
+__global__ void __launch_bounds__(256)
+half_level_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    out[i] = make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+  }
+}
+
+template <int MODE, bool V16>
+cudaError_t launch_variant(const Corr2Args& g, const Corr2Maps& maps, int num_units, int num_sms, cudaStream_t s) {
+  static DeviceOnce attr;
+  cudaError_t e = once_per_device(attr, [&] {
+    return cudaFuncSetAttribute(corr_patch_tc_kernel<MODE, V16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  if (e != cudaSuccess) return e;
+  const int grid = num_units < num_sms ? num_units : num_sms;
+  corr_patch_tc_kernel<MODE, V16><<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 bool corr_patch_supported(int T, int H4, int W4) {
@@ -473,22 +525,28 @@ bool corr_patch_supported(int T, int H4, int W4) {
   return lay.h[kL - 1] >= 8 && lay.w[kL - 1] >= 8;
 }
 
-cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_bfloat16* pyr_split, cudaStream_t s) {
+cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_bfloat16* pyr_split, int mode,
+                                 cudaStream_t s) {
   const PyramidLayout lay = pyramid_layout(T, H4, W4);
   for (int l = 0; l < kL; ++l) {
     const int64_t n = (int64_t)T * lay.h[l] * lay.w[l] * kD;
-    __nv_bfloat16* dst = pyr_split + 2 * lay.off[l];
+    __nv_bfloat16* dst = pyr_split + 2 * lay.off[l];   // level l always starts at the same offset, whatever the mode
     const int64_t n4 = n / 4;
     const int grid = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-    split_level_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(pyr + lay.off[l]),
-                                            reinterpret_cast<uint2*>(dst), reinterpret_cast<uint2*>(dst + n), n4);
+    if (mode == 3)
+      split_level_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(pyr + lay.off[l]),
+                                              reinterpret_cast<uint2*>(dst), reinterpret_cast<uint2*>(dst + n), n4);
+    else
+      half_level_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(pyr + lay.off[l]),
+                                             reinterpret_cast<uint2*>(dst), n4);
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                  const uint8_t* track_valid, const float* coords, int T, int N,
-                                 __nv_bfloat16* vol_split, int num_sms, cudaStream_t s) {
+                                 __nv_bfloat16* vol_split, int mode, int vol16, int num_sms, cudaStream_t s) {
+  if (mode < 1 || mode > 3) return cudaErrorInvalidValue;
   Corr2Args g;
   g.lay = pyramid_layout(T, H4, W4);
   g.support = support;
@@ -496,7 +554,7 @@ cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4,
   g.coords = coords;
   g.T = T;
   g.N = N;
-  g.vol = vol_split;
+  g.vol = reinterpret_cast<uint16_t*>(vol_split);
   g.trace = nullptr;
 #ifdef CT3_TRACE
   static long long* trace_buf = nullptr;
@@ -507,22 +565,22 @@ cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4,
   for (int l = 0; l < kL; ++l) {
     const uint64_t W = (uint64_t)g.lay.w[l], H = (uint64_t)g.lay.h[l];
     if (W < 8 || H < 8) return cudaErrorInvalidValue;
-    const uint64_t dims[4] = {(uint64_t)kD, W, H, (uint64_t)(2 * T)};   // dim 3 = plane*T + t
+    const uint64_t dims[4] = {(uint64_t)kD, W, H, (uint64_t)((mode == 3 ? 2 : 1) * T)};   // dim 3 = plane*T + t
     const uint64_t strides[3] = {(uint64_t)kD * 2, W * kD * 2, H * W * kD * 2};
     const uint32_t box[4] = {64, 8, 8, 1};
     if (!encode_tensor_map(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pyr_split + 2 * g.lay.off[l], dims, strides,
                            box, CU_TENSOR_MAP_SWIZZLE_128B))
       return cudaErrorInvalidValue;
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(corr_patch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
   const int num_units = N * kL;
-  const int grid = num_units < num_sms ? num_units : num_sms;
-  corr_patch_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
+  cudaError_t le;
+  if (vol16) le = mode == 3 ? launch_variant<3, true>(g, maps, num_units, num_sms, s)
+                : mode == 2 ? launch_variant<2, true>(g, maps, num_units, num_sms, s)
+                            : launch_variant<1, true>(g, maps, num_units, num_sms, s);
+  else       le = mode == 3 ? launch_variant<3, false>(g, maps, num_units, num_sms, s)
+                : mode == 2 ? launch_variant<2, false>(g, maps, num_units, num_sms, s)
+                            : launch_variant<1, false>(g, maps, num_units, num_sms, s);
+  if (le != cudaSuccess) return le;
 #ifdef CT3_TRACE
   {
     static int calls = 0;

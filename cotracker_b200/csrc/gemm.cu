@@ -16,16 +16,28 @@ namespace ct3 {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 3, ACC = 2;
-constexpr int TILE_A = BM * BK * 2;                    // 16 KiB (bf16)
+constexpr int ACC = 2;
+constexpr int TILE_A = BM * BK * 2;                    // 16 KiB (one 16-bit plane)
 constexpr int TILE_B = BN * BK * 2;                    // 16 KiB
-constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;   // hi+lo of both operands = 64 KiB
 constexpr int EPI_WARPS = 16;                          // four warps per TMEM lane quarter, a quarter of the columns each
 constexpr int CW = 16;                                 // epilogue chunk width (columns)
 constexpr int STG_WORDS = 32 * CW;                     // per-warp transpose buffer (rotated rows: conflict-free both ways)
-constexpr int OFF_STG = STAGES * STAGE_BYTES;
+constexpr int MAX_STAGES = 6;
+// Per products-per-FLOP variant: which operand planes a stage holds and how deep the ring is (always 192 KiB).
+//   3: A hi|lo, W hi|lo (64 KiB x 3)   2: A hi, W hi|lo (48 KiB x 4)   1: A hi, W hi (32 KiB x 6)
+template <int NPROD>
+struct Cfg {
+  static constexpr int AP = NPROD == 3 ? 2 : 1;
+  static constexpr int BP = NPROD >= 2 ? 2 : 1;
+  static constexpr int STAGE_BYTES = AP * TILE_A + BP * TILE_B;
+  static constexpr int STAGES = NPROD == 3 ? 3 : (NPROD == 2 ? 4 : 6);
+  static constexpr int OFF_B = AP * TILE_A;
+};
+constexpr int OFF_STG = 3 * 65536;                     // = STAGES * STAGE_BYTES of every variant
+static_assert(Cfg<1>::STAGES * Cfg<1>::STAGE_BYTES == OFF_STG && Cfg<2>::STAGES * Cfg<2>::STAGE_BYTES == OFF_STG &&
+              Cfg<3>::STAGES * Cfg<3>::STAGE_BYTES == OFF_STG, "ring size");
 constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_WORDS * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 128 /*barriers*/ + 1024 /*align slack*/;
+constexpr int SMEM_BYTES = OFF_BAR + 256 /*barriers*/ + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr uint32_t TMEM_COLS = ACC * BN;               // 256 columns (power of two)
@@ -122,14 +134,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
   }
 }
 
+template <int NPROD>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
-                      int N, int Kpad, GemmEpilogue epi) {
+                      int N, int Kpad, int fp16, GemmEpilogue epi) {
+  using C = Cfg<NPROD>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
 
@@ -171,9 +186,9 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           tma_load_2d(s, &tmX, kb * BK, mt * BM, &full_bar[stage]);
-          tma_load_2d(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
-          tma_load_2d(s + 2 * TILE_A, &tmW, kb * BK, nt * BN, &full_bar[stage]);
-          tma_load_2d(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
+          if (C::AP == 2) tma_load_2d(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
+          tma_load_2d(s + C::OFF_B, &tmW, kb * BK, nt * BN, &full_bar[stage]);
+          if (C::BP == 2) tma_load_2d(s + C::OFF_B + TILE_B, &tmW, Kpad + kb * BK, nt * BN, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -181,7 +196,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_16(BM, BN, fp16 != 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -192,15 +207,22 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
           tc_fence_after_sync();
           const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + 2 * TILE_A, b_lo = s + 2 * TILE_A + TILE_B;
+          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + C::OFF_B, b_lo = b_hi + TILE_B;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint32_t koff = kk * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle atom
-            const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
-            const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
-            umma_bf16(d_tmem, dal, dbh, idesc, (kb | kk) != 0 ? 1u : 0u);  // small terms first
-            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-            umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+            const uint32_t koff = kk * 32;  // 16 elements = 32 bytes inside the 128-byte swizzle atom
+            const uint64_t dah = umma_desc_sw128(a_hi + koff), dbh = umma_desc_sw128(b_hi + koff);
+            const uint32_t first = (kb | kk) != 0 ? 1u : 0u;
+            if (NPROD == 3) {   // small terms first
+              umma_bf16(d_tmem, umma_desc_sw128(a_lo + koff), dbh, idesc, first);
+              umma_bf16(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, 1u);
+              umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+            } else if (NPROD == 2) {
+              umma_bf16(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, first);
+              umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, dah, dbh, idesc, first);
+            }
           }
           umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -249,18 +271,20 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // both TMEMs, so the bytes ingested per FLOP halve.  Both CTAs run the same producer / epilogue code on their own
 // 128 rows; barriers: full (leader, tx from both CTAs), empty + tmem_full (multicast commit to both),
 // tmem_empty (leader, remote arrives from the peer's epilogue warps).
-template <int BNP>
+template <int BNP, int NPROD>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
-                        int N, int Kpad, GemmEpilogue epi) {
+                        int N, int Kpad, int fp16, GemmEpilogue epi) {
+  using C = Cfg<NPROD>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
   constexpr int TILE_BH = (BNP / 2) * BK * 2;                 // this CTA's half of the W tile, one plane
-  constexpr uint32_t TX_BYTES = 2u * (2u * TILE_A + 2u * TILE_BH);   // both CTAs, hi+lo of both operands
+  constexpr uint32_t TX_BYTES = 2u * ((uint32_t)C::AP * TILE_A + (uint32_t)C::BP * TILE_BH);   // both CTAs, all planes
   constexpr uint32_t TCOLS = 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
 
@@ -305,9 +329,9 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], TX_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           tma_load_2d_2sm(s, &tmX, kb * BK, mt * BM, &full_bar[stage]);
-          tma_load_2d_2sm(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
-          tma_load_2d_2sm(s + 2 * TILE_A, &tmW, kb * BK, wrow, &full_bar[stage]);
-          tma_load_2d_2sm(s + 2 * TILE_A + TILE_B, &tmW, Kpad + kb * BK, wrow, &full_bar[stage]);
+          if (C::AP == 2) tma_load_2d_2sm(s + TILE_A, &tmX, Kpad + kb * BK, mt * BM, &full_bar[stage]);
+          tma_load_2d_2sm(s + C::OFF_B, &tmW, kb * BK, wrow, &full_bar[stage]);
+          if (C::BP == 2) tma_load_2d_2sm(s + C::OFF_B + TILE_B, &tmW, Kpad + kb * BK, wrow, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -315,7 +339,7 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BNP);
+      const uint32_t idesc = umma_idesc_16(256, BNP, fp16 != 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = first; tile < num_tiles; tile += step) {
@@ -326,15 +350,22 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           mbar_wait(&full_bar[stage], phase);          // both CTAs' TMA bytes have landed
           tc_fence_after_sync();
           const uint32_t s = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + 2 * TILE_A, b_lo = s + 2 * TILE_A + TILE_B;
+          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + C::OFF_B, b_lo = b_hi + TILE_B;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint32_t koff = kk * 32;
-            const uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
-            const uint64_t dbh = umma_desc_sw128(b_hi + koff), dbl = umma_desc_sw128(b_lo + koff);
-            umma_bf16_2sm(d_tmem, dal, dbh, idesc, (kb | kk) != 0 ? 1u : 0u);
-            umma_bf16_2sm(d_tmem, dah, dbl, idesc, 1u);
-            umma_bf16_2sm(d_tmem, dah, dbh, idesc, 1u);
+            const uint64_t dah = umma_desc_sw128(a_hi + koff), dbh = umma_desc_sw128(b_hi + koff);
+            const uint32_t first = (kb | kk) != 0 ? 1u : 0u;
+            if (NPROD == 3) {
+              umma_bf16_2sm(d_tmem, umma_desc_sw128(a_lo + koff), dbh, idesc, first);
+              umma_bf16_2sm(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, 1u);
+              umma_bf16_2sm(d_tmem, dah, dbh, idesc, 1u);
+            } else if (NPROD == 2) {
+              umma_bf16_2sm(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, first);
+              umma_bf16_2sm(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16_2sm(d_tmem, dah, dbh, idesc, first);
+            }
           }
           umma_commit_2sm(&empty_bar[stage]);          // frees the stage in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -399,20 +430,24 @@ __device__ __forceinline__ void epilogue_store1(const GemmEpilogue& e, int N, in
 
 __global__ void __launch_bounds__(256)
 gemm_split3_simt_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ W, int M, int N,
-                        int Kpad, GemmEpilogue epi) {
+                        int Kpad, int64_t x_ld, int products, int fp16, GemmEpilogue epi) {
   __shared__ float As[16][64 + 1];
   __shared__ float Bs[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4] = {};
   const int64_t ld = 2 * (int64_t)Kpad;
+  // the planes the tensor-core path multiplies: x_hi (+ x_lo when 3 products), w_hi (+ w_lo when >= 2 products)
+  auto val = [fp16](const __nv_bfloat16* p) {
+    return fp16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*p);
+  };
   for (int k0 = 0; k0 < Kpad; k0 += 16) {
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
       const int r = i >> 4, k = i & 15;
       const int gm = m0 + r, gn = n0 + r;
       float a = 0.f, b = 0.f;
-      if (gm < M) a = __bfloat162float(X[gm * ld + k0 + k]) + __bfloat162float(X[gm * ld + Kpad + k0 + k]);
-      if (gn < N) b = __bfloat162float(W[gn * ld + k0 + k]) + __bfloat162float(W[gn * ld + Kpad + k0 + k]);
+      if (gm < M) a = val(X + gm * x_ld + k0 + k) + (products == 3 ? val(X + gm * x_ld + Kpad + k0 + k) : 0.f);
+      if (gn < N) b = val(W + gn * ld + k0 + k) + (products >= 2 ? val(W + gn * ld + Kpad + k0 + k) : 0.f);
       As[k][r] = a;
       Bs[k][r] = b;
     }
@@ -443,16 +478,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const EncodeTiledFn fn = [] {   // C++11 thread-safe one-time initialisation
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
@@ -484,10 +517,62 @@ bool encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int rank, cons
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+namespace {
+
+template <int NPROD>
+cudaError_t set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel<NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_pair_kernel<256, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_pair_kernel<192, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  return e;
+}
+
+template <int NPROD>
+cudaError_t launch_tc(const GemmProblem& p, const CUtensorMap& tmX, const CUtensorMap& tmW, int bnp, int num_mt,
+                      int num_sms, cudaStream_t stream) {
+  if (bnp == 0) {
+    const int num_tiles = num_mt * (p.N / BN);
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    gemm_split3_tc_kernel<NPROD><<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.fp16, p.epi);
+    return cudaGetLastError();
+  }
+  const int groups = ((num_mt + 1) / 2) * (p.N / bnp);
+  int pairs = num_sms / 2;
+  if (pairs > groups) pairs = groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = (bnp == 256)
+      ? cudaLaunchKernelEx(&cfg, gemm_split3_pair_kernel<256, NPROD>, tmX, tmW, p.M, p.N, p.Kpad, p.fp16, p.epi)
+      : cudaLaunchKernelEx(&cfg, gemm_split3_pair_kernel<192, NPROD>, tmX, tmW, p.M, p.N, p.Kpad, p.fp16, p.epi);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
 int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream, const char** err) {
   *err = nullptr;
   if (p.M <= 0 || p.N <= 0 || p.Kpad <= 0 || (p.N % BN) != 0 || (p.Kpad % BK) != 0) {
     *err = "gemm: need M>0, N % 128 == 0, Kpad % 64 == 0";
+    return (int)cudaErrorInvalidValue;
+  }
+  if (p.products < 1 || p.products > 3) {
+    *err = "gemm: products must be 1, 2 or 3";
+    return (int)cudaErrorInvalidValue;
+  }
+  const int64_t x_ld = p.x_ld ? p.x_ld : 2 * (int64_t)p.Kpad;
+  if (x_ld < (p.products == 3 ? 2 : 1) * (int64_t)p.Kpad || (x_ld % 8) != 0) {
+    *err = "gemm: x_ld too small for the operand planes this product count reads";
     return (int)cudaErrorInvalidValue;
   }
   if ((reinterpret_cast<uintptr_t>(p.x_split) | reinterpret_cast<uintptr_t>(p.w_split)) & 15) {
@@ -496,7 +581,8 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
   }
   if (impl == 1) {
     dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
-    gemm_split3_simt_kernel<<<grid, 256, 0, stream>>>(p.x_split, p.w_split, p.M, p.N, p.Kpad, p.epi);
+    gemm_split3_simt_kernel<<<grid, 256, 0, stream>>>(p.x_split, p.w_split, p.M, p.N, p.Kpad, x_ld, p.products,
+                                                      p.fp16, p.epi);
     return (int)cudaGetLastError();
   }
   const int num_mt = (p.M + BM - 1) / BM;
@@ -504,45 +590,25 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
   int bnp = 0;
   if (impl == 0 && num_mt >= 2 * num_sms) bnp = (p.N % 256 == 0) ? 256 : ((p.N % 192 == 0) ? 192 : 0);
   CUtensorMap tmX, tmW;
-  if (!make_tmap(&tmX, p.x_split, (uint64_t)p.M, 2ull * p.Kpad) ||
+  if (!make_tmap(&tmX, p.x_split, (uint64_t)p.M, (uint64_t)x_ld) ||
       !make_tmap(&tmW, p.w_split, (uint64_t)p.N, 2ull * p.Kpad, bnp ? (uint32_t)(bnp / 2) : 128u)) {
     *err = "gemm: cuTensorMapEncodeTiled failed";
     return (int)cudaErrorInvalidValue;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_split3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_split3_pair_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  static DeviceOnce attr_set;
+  {
+    cudaError_t e = once_per_device(attr_set, [&] {
+      cudaError_t e = set_attrs<3>();
+      if (e == cudaSuccess) e = set_attrs<2>();
+      if (e == cudaSuccess) e = set_attrs<1>();
+      return e;
+    });
     if (e != cudaSuccess) { *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed"; return (int)e; }
-    attr_set = true;
   }
-  if (bnp == 0) {
-    const int num_tiles = num_mt * (p.N / BN);
-    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-    gemm_split3_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW, p.M, p.N, p.Kpad, p.epi);
-  } else {
-    const int groups = ((num_mt + 1) / 2) * (p.N / bnp);
-    int pairs = num_sms / 2;
-    if (pairs > groups) pairs = groups;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = (bnp == 256)
-        ? cudaLaunchKernelEx(&cfg, gemm_split3_pair_kernel<256>, tmX, tmW, p.M, p.N, p.Kpad, p.epi)
-        : cudaLaunchKernelEx(&cfg, gemm_split3_pair_kernel<192>, tmX, tmW, p.M, p.N, p.Kpad, p.epi);
-    if (e != cudaSuccess) return (int)e;
-  }
-  return (int)cudaGetLastError();
+  cudaError_t e = p.products == 3 ? launch_tc<3>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
+                : p.products == 2 ? launch_tc<2>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
+                                  : launch_tc<1>(p, tmX, tmW, bnp, num_mt, num_sms, stream);
+  return (int)e;
 }
 
 }  // namespace ct3

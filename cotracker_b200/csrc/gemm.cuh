@@ -28,9 +28,16 @@ struct GemmEpilogue {
 };
 
 struct GemmProblem {
-  const __nv_bfloat16* x_split;  // [M, 2*Kpad]
+  const __nv_bfloat16* x_split;  // [M, x_ld]: hi plane at column 0, lo plane (if any) at column Kpad
   const __nv_bfloat16* w_split;  // [N, 2*Kpad]
   int M, N, Kpad;                // N % 128 == 0, Kpad % 64 == 0
+  // Tensor-core products per FLOP (precision switch):
+  //   3 : hi*hi + lo*hi + hi*lo   (both operands split; rel. error ~2^-17 bf16 / ~2^-22 fp16)
+  //   2 : x_hi*w_hi + x_hi*w_lo   (activation rounded to its hi plane, weights exact to the split)
+  //   1 : x_hi*w_hi
+  int products = 3;
+  int fp16 = 0;                  // operand planes hold IEEE fp16 (11-bit significand) instead of bf16 (8-bit)
+  int64_t x_ld = 0;              // row pitch of x in elements; 0 = 2*Kpad.  Kpad for a single-plane (hi only) operand
   GemmEpilogue epi;
 };
 

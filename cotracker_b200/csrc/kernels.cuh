@@ -33,9 +33,13 @@ cudaError_t launch_upsample_concat(const float* const src[4], const int c[4], co
 // vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level
 // impl: 0 tensor cores (corr_tc2.cu when pyr_split is given and every level is >= 8x8, else corr_tc.cu),
 //       1 exact-fp32 SIMT, 2 corr_tc.cu always
+// mode / vol16 apply to the corr_tc2.cu path only (corr_uses_patch_kernel): products per correlation FLOP (3|2|1;
+// pyr_split must have been made with the same mode) and a single-fp16-plane volume [N*T*4, kVolPad] instead of the
+// split one; the other kernels always compute in fp32 / bf16x3 and write the split volume.
+bool corr_uses_patch_kernel(int impl, bool have_pyr_split, int T, int H4, int W4);
 cudaError_t launch_corr_sample(const float* pyr, const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                const uint8_t* track_valid, const float* coords, int T, int N,
-                               __nv_bfloat16* vol_split, int impl, int num_sms, cudaStream_t s);
+                               __nv_bfloat16* vol_split, int impl, int mode, int vol16, int num_sms, cudaStream_t s);
 
 cudaError_t launch_corr_sample_tc(const float* pyr, int H4, int W4, const float* support,
                                   const uint8_t* track_valid, const float* coords, int T, int N,
@@ -44,10 +48,12 @@ cudaError_t launch_corr_sample_tc(const float* pyr, int H4, int W4, const float*
 // corr_tc2.cu: correlate-then-interpolate on a split-bf16 copy of the pyramid
 //   pyr_split: per level at bf16 offset 2*off[l]: [plane hi|lo][T][H][W][128]   (same bytes as the fp32 pyramid)
 bool corr_patch_supported(int T, int H4, int W4);
-cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_bfloat16* pyr_split, cudaStream_t s);
+//   mode 3: [plane hi|lo][T][H][W][128] bf16;  mode 1/2: one fp16 plane [T][H][W][128] at the same level offset
+cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_bfloat16* pyr_split, int mode,
+                                 cudaStream_t s);
 cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                  const uint8_t* track_valid, const float* coords, int T, int N,
-                                 __nv_bfloat16* vol_split, int num_sms, cudaStream_t s);
+                                 __nv_bfloat16* vol_split, int mode, int vol16, int num_sms, cudaStream_t s);
 
 // ---- tokens.cu : elementwise / row-wise pieces of the transformer ---------------------------------
 cudaError_t launch_layernorm_split(const float* x, int rows, const float* gamma, const float* beta, float eps,
@@ -60,8 +66,9 @@ cudaError_t launch_heads(const float* tokens, const float* w4, const float* b4, 
                          float* conf, float* delta_out, int T, int N, cudaStream_t s);
 cudaError_t launch_row_bias(const float* time_emb, const float* w_in, int T, float* out, cudaStream_t s);
 // fp32 [rows,K] -> split [rows, 2*Kpad]; perm_x: apply the X column permutation (x_src_col)
+// fp16 != 0: the planes hold IEEE fp16 (hi = fp16(x), lo = fp16(x - hi)) instead of bf16
 cudaError_t launch_split_rows(const float* x, int rows, int K, int Kpad, int perm_x, __nv_bfloat16* out,
-                              int64_t dst_row_off, cudaStream_t s);
+                              int64_t dst_row_off, cudaStream_t s, int fp16 = 0);
 
 // ---- attention.cu -------------------------------------------------------------------------------
 struct AttnParams {

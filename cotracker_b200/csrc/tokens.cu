@@ -154,7 +154,7 @@ row_bias_kernel(const float* __restrict__ te, const float* __restrict__ w, int T
   if (lane == 0) out[o] = acc;
 }
 
-__global__ void split_rows_kernel(const float* __restrict__ x, int rows, int K, int Kpad, int perm_x,
+__global__ void split_rows_kernel(const float* __restrict__ x, int rows, int K, int Kpad, int perm_x, int fp16,
                                   __nv_bfloat16* __restrict__ out, int64_t dst_row_off) {
   const int64_t total = (int64_t)rows * Kpad;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -163,10 +163,16 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int rows, int K, 
     const int64_t r = idx / Kpad;
     const int sc = perm_x ? x_src_col(c) : (c < K ? c : -1);
     const float v = sc >= 0 ? x[r * K + sc] : 0.f;
-    const bf16pair p = split_bf16(v);
     __nv_bfloat16* o = out + (dst_row_off + r) * (2 * (int64_t)Kpad) + c;
-    o[0] = p.hi;
-    o[Kpad] = p.lo;
+    if (fp16) {
+      const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+      reinterpret_cast<__half*>(o)[0] = hi;
+      reinterpret_cast<__half*>(o)[Kpad] = lo;
+    } else {
+      const bf16pair p = split_bf16(v);
+      o[0] = p.hi;
+      o[Kpad] = p.lo;
+    }
   }
 }
 
@@ -203,9 +209,9 @@ cudaError_t launch_row_bias(const float* time_emb, const float* w_in, int T, flo
   return cudaGetLastError();
 }
 cudaError_t launch_split_rows(const float* x, int rows, int K, int Kpad, int perm_x, __nv_bfloat16* out,
-                              int64_t dst_row_off, cudaStream_t s) {
+                              int64_t dst_row_off, cudaStream_t s, int fp16) {
   if (rows <= 0) return cudaSuccess;
-  split_rows_kernel<<<grid_for((int64_t)rows * Kpad, 256), 256, 0, s>>>(x, rows, K, Kpad, perm_x, out, dst_row_off);
+  split_rows_kernel<<<grid_for((int64_t)rows * Kpad, 256), 256, 0, s>>>(x, rows, K, Kpad, perm_x, fp16, out, dst_row_off);
   return cudaGetLastError();
 }
 

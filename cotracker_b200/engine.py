@@ -34,6 +34,7 @@ def _declare(lib):
         "ct3_last_error": (c_char_p, []),
         "ct3_set_option": (c_int, [c_char_p, c_int]),
         "ct3_get_option": (c_int, [c_char_p, intp]),
+        "ct3_precision_info": (c_int, [c_int, c_int, c_int, intp, intp, intp]),
         "ct3_num_weight_tensors": (c_int, []),
         "ct3_weight_name": (c_char_p, [c_int]),
         "ct3_packed_weights_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
@@ -48,6 +49,8 @@ def _declare(lib):
                                     c_size_t, c_void_p]),
         "ct3_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_split_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_split_rows_fp16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+        "ct3_linear_prec": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_updateformer": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
         "ct3_upsample_concat": (c_int, [ctypes.POINTER(c_void_p), intp, intp, intp, c_int, c_int, c_int, c_void_p, c_void_p]),
         "ct3_enc_tail_packed_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
@@ -65,10 +68,10 @@ def _declare(lib):
 
 
 EXPORTED_SYMBOLS = [
-    "ct3_version", "ct3_last_error", "ct3_set_option", "ct3_get_option", "ct3_num_weight_tensors",
+    "ct3_version", "ct3_last_error", "ct3_set_option", "ct3_get_option", "ct3_precision_info", "ct3_num_weight_tensors",
     "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
     "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
-    "ct3_corr_sample", "ct3_linear", "ct3_split_rows", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
+    "ct3_corr_sample", "ct3_linear", "ct3_linear_prec", "ct3_split_rows", "ct3_split_rows_fp16", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
     "ct3_upsample_concat", "ct3_enc_tail_packed_bytes", "ct3_enc_tail_pack", "ct3_enc_tail_workspace_bytes", "ct3_enc_tail",
 ]
 
@@ -122,6 +125,26 @@ def get_option(name: str) -> int:
     v = ctypes.c_int(0)
     _check(lib().ct3_get_option(name.encode(), ctypes.byref(v)), f"ct3_get_option({name})")
     return v.value
+
+
+def precision_info(T: int = 16, H4: int = 96, W4: int = 128):
+    """-> (corr_products, fc1_products, volume_bytes_per_element) in effect for this thread's options."""
+    a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _check(lib().ct3_precision_info(T, H4, W4, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "ct3_precision_info")
+    return a.value, b.value, c.value
+
+
+def precision_summary(T: int = 16, H4: int = 96, W4: int = 128) -> dict:
+    """What bench.py prints as `dtype`: the arithmetic each GEMM group computes in (no precision claim beyond it)."""
+    corr, fc1, vb = precision_info(T, H4, W4)
+    name = {3: "x3 (split x split: hi*hi+lo*hi+hi*lo)", 2: "x2 (fp16 plane x split fp16)", 1: "x1 (single fp16 product)"}
+    return {
+        "dtype": (f"transformer + corr_mlp.fc2 + input_transform: bf16x3; correlation einsum: "
+                  f"{'bf16' if corr == 3 else 'fp16'}{name[corr][:2]}; corr_mlp.fc1: {'bf16' if fc1 == 3 else 'fp16'}"
+                  f"{name[fc1][:2]}; fp32 accumulate, fp32 softmax/LayerNorm/GELU"),
+        "products": f"3 (bf16 split) except correlation einsum {corr} and corr_mlp.fc1 {fc1}",
+        "corr_products": corr, "fc1_products": fc1, "volume_bytes_per_element": vb,
+    }
 
 
 def weight_names() -> List[str]:
@@ -237,36 +260,45 @@ def corr_sample(pyr, H4, W4, support, track_valid, coords, scratch: bool = True)
     """-> fp32 correlation volume [N, T, 4, 2401] reconstructed from the split-bf16 device layout.
     scratch=False withholds the split-pyramid scratch, i.e. selects the sample-then-correlate kernel."""
     T, N, _ = coords.shape
-    vol = torch.empty(N * T * LEVELS, 2 * VOL_PAD, dtype=torch.bfloat16, device=coords.device)
+    vol = torch.zeros(N * T * LEVELS, 2 * VOL_PAD, dtype=torch.bfloat16, device=coords.device)
     scr = torch.empty(pyr.numel() * 4, dtype=torch.uint8, device=coords.device) if scratch else None
+    # a single fp16 plane [rows, 2432] when the correlate-then-interpolate kernel runs with prec.fc1 < 3
+    vb = precision_info(T, H4, W4)[2] if (scratch and get_option("corr") == 0) else 4
     with torch.cuda.device(coords.device):
         _check(lib().ct3_corr_sample(_ptr(pyr), H4, W4, _ptr(support), _ptr(track_valid), _ptr(coords), T, N, _ptr(vol),
                                      _ptr(scr), scr.numel() if scratch else 0, _stream(coords.device)),
                "ct3_corr_sample")
-    v = vol.float()
-    full = v[:, :VOL_PAD] + v[:, VOL_PAD:]
+    if vb == 2:
+        full = vol.reshape(-1).view(torch.float16)[:N * T * LEVELS * VOL_PAD].reshape(-1, VOL_PAD).float()
+    else:
+        v = vol.float()
+        full = v[:, :VOL_PAD] + v[:, VOL_PAD:]
     assert bool((full[:, VOL:] == 0).all()), "K padding of the correlation volume must be zero"
     return full[:, :VOL].reshape(N, T, LEVELS, VOL)
 
 
-def split_rows(x: torch.Tensor, Kpad: int) -> torch.Tensor:
+def split_rows(x: torch.Tensor, Kpad: int, fp16: bool = False) -> torch.Tensor:
     _req(x, torch.float32, "x")
     rows, K = x.shape
-    out = torch.empty(rows, 2 * Kpad, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(rows, 2 * Kpad, dtype=torch.bfloat16, device=x.device)   # 16-bit planes (bf16 or fp16 bits)
+    fn = lib().ct3_split_rows_fp16 if fp16 else lib().ct3_split_rows
     with torch.cuda.device(x.device):
-        _check(lib().ct3_split_rows(_ptr(x), rows, K, Kpad, _ptr(out), _stream(x.device)), "ct3_split_rows")
+        _check(fn(_ptr(x), rows, K, Kpad, _ptr(out), _stream(x.device)), "ct3_split_rows")
     return out
 
 
-def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
-    """Y = act(x w^T + b) through the split-bf16x3 engine; x [M,K], w [Nout,K] fp32."""
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0, products: int = 3,
+           fp16: bool = False) -> torch.Tensor:
+    """Y = act(x w^T + b) through the tcgen05 GEMM engine; x [M,K], w [Nout,K] fp32.  products / fp16: the
+    precision switches (3 = split x split, 2 = x_hi x split w, 1 = x_hi x w_hi; bf16 or fp16 planes)."""
     M, K = x.shape
     Nout = w.shape[0]
     Kpad = (K + 63) // 64 * 64
-    xs, ws = split_rows(x.contiguous(), Kpad), split_rows(w.contiguous(), Kpad)
+    xs, ws = split_rows(x.contiguous(), Kpad, fp16), split_rows(w.contiguous(), Kpad, fp16)
     y = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _check(lib().ct3_linear(_ptr(xs), _ptr(ws), _ptr(bias), M, Nout, Kpad, act, _ptr(y), _stream(x.device)), "ct3_linear")
+        _check(lib().ct3_linear_prec(_ptr(xs), _ptr(ws), _ptr(bias), M, Nout, Kpad, act, products, 1 if fp16 else 0,
+                                     _ptr(y), _stream(x.device)), "ct3_linear_prec")
     return y
 
 

@@ -96,6 +96,9 @@ class CoTrackerThreeBase(nn.Module):
                 or not linear_layer_for_vis_conf:
             raise NotImplementedError("libct3_b200 implements the released CoTracker3 configuration only "
                                       "(stride 4, radius 3, 4 levels, 64 virtual tracks)")
+        if tuple(model_resolution) != (384, 512):
+            # the relative-motion posenc is normalised by model_resolution/stride = (128, 96) inside tokens.cu
+            raise NotImplementedError("libct3_b200 hard-codes model_resolution=(384, 512) (posenc scale 128/96)")
         self.window_len = window_len
         self.stride = stride
         self.corr_radius = corr_radius
@@ -222,7 +225,7 @@ class CoTrackerThreeOnline(CoTrackerThreeBase):
         self.online_coords_predicted = None
         self.online_vis_predicted = None
         self.online_conf_predicted = None
-        self._online_enc_cache = None             # (frames, pyramid) of the previous chunk
+        self._online_enc_cache = None             # (per-frame checksums, pyramid) of the previous chunk
 
     def _encode_online(self, frames, chunk, step, H4, W4):
         """Consecutive online chunks overlap by window_len - step frames and the encoder is strictly per-frame
@@ -231,16 +234,32 @@ class CoTrackerThreeOnline(CoTrackerThreeBase):
         S = frames.shape[0]
         keep = S - step
         cache = getattr(self, "_online_enc_cache", None)
+        sig = self._frame_signatures(frames)           # [S,2] float64: one pass over the chunk, 16 numbers to the host
         pyr = None
         if cache is not None and self.online_ind > 0 and keep > 0:
-            prev_frames, prev_pyr = cache
-            if prev_frames.shape == frames.shape and torch.equal(frames[:keep], prev_frames[step:]):
+            prev_sig, prev_shape, prev_pyr = cache
+            if prev_shape == frames.shape and torch.equal(sig[:keep], prev_sig[step:]):
                 new = self._encode(frames[keep:].contiguous(), chunk)
                 pyr = engine.concat_pyramid_frames(prev_pyr, S, step, new, S - keep, H4, W4)
         if pyr is None:
             pyr = self._encode(frames, chunk)
-        self._online_enc_cache = (frames, pyr)
+        self._online_enc_cache = (sig, frames.shape, pyr)
         return pyr
+
+    def _frame_signatures(self, frames: torch.Tensor) -> torch.Tensor:
+        """Two order-sensitive checksums per frame (plain sum and a position-weighted sum, float64 accumulators):
+        frames whose signatures match the previous chunk's are taken to be the same frames.  Replaces a full
+        `torch.equal` against a retained 38 MB copy of the previous chunk."""
+        S = frames.shape[0]
+        flat = frames.reshape(S, -1)
+        key = (flat.shape[1], str(flat.device))
+        if getattr(self, "_sig_key", None) != key:
+            g = torch.Generator().manual_seed(0x5eed)
+            self._sig_w = torch.rand(flat.shape[1], generator=g, dtype=torch.float32).to(flat.device)
+            self._sig_key = key
+        a = flat.sum(dim=1, dtype=torch.float64)
+        b = (flat * self._sig_w).sum(dim=1, dtype=torch.float64)
+        return torch.stack([a, b], dim=1)
 
     @torch.no_grad()
     def forward(self, video, queries, iters=4, is_train=False, add_space_attn=True, fmaps_chunk_size=200,

@@ -19,7 +19,7 @@
  *   - all work is enqueued on the given cudaStream_t and is asynchronous w.r.t.
  *     the host; B (batch) is 1 as in the reference (cotracker3_offline.py:135,141).
  *
- * Symbols (all extern "C"):  see the declarations below; tests/test_abi.py checks
+ * Symbols (all extern "C"):  see the declarations below; tests/test_host_logic.py checks
  * that the built library exports each of them.
  */
 #ifndef CT3_B200_H_
@@ -75,6 +75,12 @@ const char* ct3_last_error(void);
  * sample-then-correlate tensor-core kernel that otherwise only serves pyramids with a level below 8x8). */
 int ct3_set_option(const char* name, int value);
 int ct3_get_option(const char* name, int* value);
+/* Precision switches of the correlation branch ("prec.corr", "prec.fc1": tensor-core products per FLOP, 3 | 2 | 1;
+ * DESIGN.md section 2).  Options and the live profiler are per HOST THREAD (thread_local), values are range-checked.
+ * ct3_precision_info reports what actually runs for a (T, H4, W4) problem under the calling thread's options:
+ * products of the 49x128x49 correlation contraction (cotracker3_offline.py:148-156), of corr_mlp.fc1
+ * (blocks.py:61), and the bytes per element of the correlation volume (4 = split bf16 hi|lo, 2 = one fp16 plane). */
+int ct3_precision_info(int T, int H4, int W4, int* corr_products, int* fc1_products, int* volume_bytes_per_element);
 
 /* ---- one-time weight packing ------------------------------------------------
  * Replaces the nn.Module parameter storage read by cotracker3_online.py:73-92.
@@ -169,8 +175,14 @@ int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support,
 int ct3_linear(const void* x_split, const void* w_split, const float* bias, int M, int Nout,
                int Kpad, int act, float* y, ct3_stream_t stream);
 
-/* fp32 [rows, K] -> split bf16 [rows, 2*Kpad] (zero padded) */
+/* Same with the precision switches of the GEMM engine: `products` tensor-core products per FLOP (3: split x split,
+ * 2: x_hi x (w_hi + w_lo), 1: x_hi x w_hi) on bf16 (fp16 = 0) or IEEE-fp16 (fp16 = 1) planes. */
+int ct3_linear_prec(const void* x_split, const void* w_split, const float* bias, int M, int Nout,
+                    int Kpad, int act, int products, int fp16, float* y, ct3_stream_t stream);
+
+/* fp32 [rows, K] -> split bf16 [rows, 2*Kpad] (zero padded); _fp16: the planes hold IEEE fp16 instead */
 int ct3_split_rows(const float* x, int rows, int K, int Kpad, void* x_split, ct3_stream_t stream);
+int ct3_split_rows_fp16(const float* x, int rows, int K, int Kpad, void* x_split, ct3_stream_t stream);
 
 /* One EfficientUpdateFormer forward (cotracker.py:483-531) on an explicit token
  * input x [N, T, 1110] fp32 (time embedding already added, reference column order);

@@ -43,6 +43,30 @@ def test_linear_matches_fp64(eng, impl, M, K, N):
     assert _rel_err(got, want) < 2e-5, (impl, M, K, N, _rel_err(got, want))
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("products,fp16,tol", [(3, 1, 1e-5), (2, 1, 6e-4), (1, 1, 1.2e-3), (2, 0, 8e-3), (1, 0, 1.6e-2)])
+@pytest.mark.parametrize("M,K,N", [(300, 384, 384), (1000, 2401, 384), (40100, 2401, 384)])
+def test_linear_precision_variants(eng, impl, products, fp16, tol, M, K, N):
+    """The GEMM engine's precision switches against fp64: fp16 planes x3 ~2^-22, x2 = activation rounded to fp16
+    (2^-12, weights exact), x1 = both rounded; bf16 planes: 2^-9.  Bounds are a few times the rounding of ONE operand
+    element relative to the output scale (errors average over K).  Also checks tensor-core == SIMT restatement."""
+    g = torch.Generator().manual_seed(M + K + products)
+    x = torch.rand(M, K, generator=g) * 2 - 1                      # correlations live in [-1, 1]
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    want = x.double() @ w.double().t() + b.double()
+    eng.set_option("gemm", impl)
+    try:
+        got = eng.linear(x.to(DEV), w.to(DEV), b.to(DEV), act=0, products=products, fp16=bool(fp16))
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("gemm", 0)
+    err = _rel_err(got, want)
+    assert err < tol, (impl, products, fp16, M, K, N, err)
+    if products < 3:
+        assert err > tol / 200, "suspiciously exact: is the lo plane still being multiplied?"
+
+
 @pytest.mark.parametrize("act,approx", [(1, "none"), (2, "tanh")])
 def test_linear_gelu_epilogues(eng, act, approx):
     g = torch.Generator().manual_seed(act)
@@ -133,6 +157,38 @@ def test_corr_sample(eng, impl, T, N, H4, W4):
         err = float((got[:, :, l].permute(1, 0, 2) - want).abs().max())
         assert err < 5e-5, (impl, l, err)   # |corr| <= 1; grid_sample normalise/denormalise noise ~1e-5, bf16x3 ~1e-5
     assert bool((got[dead] == 0).all())
+
+
+# precision switches of the correlate-then-interpolate kernel: products of the contraction x volume format.
+# tolerances: texels rounded to fp16 -> ~2^-12 * sqrt(128) * |f||s| / 128 ~ 3e-5 on top of the 5e-5 above;
+# a single fp16 volume plane rounds |v| <= 1 to 2^-12 relative -> 2.5e-4.
+@pytest.mark.parametrize("corr,fc1,tol", [(2, 3, 1.2e-4), (1, 3, 1.5e-4), (3, 2, 3.2e-4), (2, 2, 3.6e-4), (1, 1, 4e-4)])
+@pytest.mark.parametrize("T,N,H4,W4", [(2, 9, 8, 8), (5, 33, 96, 128), (16, 300, 96, 128), (3, 150, 64, 72)])
+def test_corr_sample_precision_modes(eng, corr, fc1, tol, T, N, H4, W4):
+    fmaps = _pyramid_case(T, H4, W4, seed=2)
+    want_pyr = O.normalized_pyramid(fmaps)
+    pyr = eng.prepare_pyramid(fmaps.to(DEV))
+    g = torch.Generator().manual_seed(11)
+    support = torch.randn(4, 49, N, 128, generator=g)
+    support = support / support.norm(dim=-1, keepdim=True)
+    coords = _coords_case(T, N, H4, W4, 13)
+    valid = torch.ones(N, dtype=torch.uint8)
+    valid[min(5, N - 1)] = 0
+    c0, f0 = eng.get_option("prec.corr"), eng.get_option("prec.fc1")
+    eng.set_option("prec.corr", corr)
+    eng.set_option("prec.fc1", fc1)
+    try:
+        assert eng.precision_info(T, H4, W4) == (corr, fc1, 4 if fc1 == 3 else 2)
+        got = eng.corr_sample(pyr, H4, W4, support.to(DEV), valid.to(DEV), coords.to(DEV)).cpu()
+    finally:
+        eng.set_option("prec.corr", c0)
+        eng.set_option("prec.fc1", f0)
+    worst = 0.0
+    for l in range(4):
+        want = O.correlation_volume(want_pyr[l], support[l] * valid[None, :, None].float(), coords / 2 ** l)
+        worst = max(worst, float((got[:, :, l].permute(1, 0, 2) - want).abs().max()))
+    assert worst < tol, (corr, fc1, worst)
+    assert bool((got[min(5, N - 1)] == 0).all())
 
 
 def _amplified_sd(seed=1234, **kw):

@@ -161,3 +161,47 @@ def test_corr_patch_taps_stay_in_box():
             s0 = x0 - origin
             s1 = np.where(w > 0, x1 - origin, s0)
             assert s0.min() >= 0 and s0.max() <= 7 and s1.min() >= 0 and s1.max() <= 7, (size, a)
+
+
+def test_dropin_package_and_hub_entry_points():
+    """The import-path shim (dropin/cotracker/...) and hubconf.py expose the reference's names:
+    `from cotracker.predictor import CoTrackerPredictor`, `build_cotracker`, `torch.hub.load(..., source="local")`."""
+    code = (
+        "import torch, cotracker\n"
+        "from cotracker.predictor import CoTrackerPredictor, CoTrackerOnlinePredictor\n"
+        "from cotracker.models.build_cotracker import build_cotracker\n"
+        "from cotracker.models.core.cotracker.cotracker3_offline import CoTrackerThreeOffline\n"
+        "from cotracker.models.core.cotracker.cotracker3_online import CoTrackerThreeOnline\n"
+        "import cotracker_b200.predictor as P\n"
+        "assert CoTrackerPredictor is P.CoTrackerPredictor and CoTrackerOnlinePredictor is P.CoTrackerOnlinePredictor\n"
+        "m = build_cotracker(None, offline=False, window_len=16)\n"
+        "assert isinstance(m, CoTrackerThreeOnline) and m.window_len == 16 and m.model_resolution == (384, 512)\n"
+        "on = torch.hub.load(%r, 'cotracker3_online', source='local', pretrained=False)\n"
+        "off = torch.hub.load(%r, 'cotracker3_offline', source='local', pretrained=False)\n"
+        "assert type(on).__name__ == 'CoTrackerOnlinePredictor' and on.step == 8 and on.model.window_len == 16\n"
+        "assert type(off).__name__ == 'CoTrackerPredictor' and off.model.window_len == 60 and off.interp_shape == (384, 512)\n"
+        "print('HUB_OK')\n" % (ROOT, ROOT))
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "dropin") + os.pathsep + ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240, env=env, cwd="/tmp")
+    assert r.returncode == 0 and "HUB_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_non_default_model_resolution_is_rejected():
+    """tokens.cu normalises the relative-motion posenc by (128, 96) = (512, 384)/4."""
+    from cotracker_b200.model import CoTrackerThreeOffline
+    with pytest.raises(NotImplementedError):
+        CoTrackerThreeOffline(window_len=60, model_resolution=(256, 320))
+
+
+def test_options_are_validated_and_thread_local():
+    import threading
+    from cotracker_b200 import engine
+    lib = engine.lib()
+    assert lib.ct3_set_option(b"corr", 7) == -1 and b"out of range" in lib.ct3_last_error()
+    assert lib.ct3_set_option(b"attn", -1) == -1
+    assert lib.ct3_set_option(b"gemm", 1) == 0 and engine.get_option("gemm") == 1
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(engine.get_option("gemm")))   # another host thread: defaults
+    t.start(); t.join()
+    assert seen == [0]
+    assert lib.ct3_set_option(b"gemm", 0) == 0

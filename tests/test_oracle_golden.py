@@ -4,7 +4,10 @@ import torch
 
 from cases import CASES, compare, load_golden, run_oracle
 
-ORACLE_CASES = [n for n, c in CASES.items() if c["kind"] != "predictor_online"]
+# the CPU suite must stay within minutes: the BASELINE-scale fixtures (c1/c4/headline: 16 s ... 2 min of CPU each) and
+# the dense pass (1 min) are checked on the GPU only; C2 (grid 30, 512x512x16) is the full-size case run here.
+SLOW = ("c1_", "c4_", "headline_", "pred_dense", "c2_grid30_stress")
+ORACLE_CASES = [n for n in CASES if not n.startswith(SLOW)]
 
 
 @pytest.mark.parametrize("name", ORACLE_CASES)
