@@ -19,7 +19,7 @@ thread_local char g_err[512] = "";
 // Options and the profiler are PER HOST THREAD (thread_local): a thread that drives its own GPU/stream never sees
 // another thread's verification switches or profile records.
 struct OptDef { const char* name; int lo, hi; };
-enum { OPT_GEMM = 0, OPT_CORR, OPT_ATTN, OPT_PREC_CORR, OPT_PREC_FC1, OPT_COUNT };
+enum { OPT_GEMM = 0, OPT_CORR, OPT_ATTN, OPT_PREC_CORR, OPT_PREC_FC1, OPT_FUSE, OPT_COUNT };
 constexpr int kDefPrecCorr = 3, kDefPrecFc1 = 3;
 constexpr OptDef kOptDefs[OPT_COUNT] = {
     {"gemm", 0, 1},   // 0 tcgen05, 1 SIMT verification
@@ -30,8 +30,9 @@ constexpr OptDef kOptDefs[OPT_COUNT] = {
     // switch: SURVEY 7.3 measured that every transformer GEMM breaks the 1e-3 px budget with fewer than 3 products.
     {"prec.corr", 1, 3},   // the 49x128x49 correlation contraction (corr_tc2.cu)
     {"prec.fc1", 1, 3},    // corr_mlp.fc1 (K = 2401): 1|2 also make the correlation volume a single fp16 plane
+    {"fuse", 0, 1},        // 1: q|k|v projection + time attention in one kernel (gemm_qkv_time_attn_kernel); 0: separate
 };
-thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1};
+thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1, 1};
 #define g_opt_gemm g_opt[OPT_GEMM]
 #define g_opt_corr g_opt[OPT_CORR]
 #define g_opt_attn g_opt[OPT_ATTN]
@@ -90,6 +91,7 @@ struct Lin {
   int N = 0, K = 0, Kpad = 0;
 };
 struct Block {
+  Lin qkv_h;  // time blocks only: q|k|v regrouped per head, rows h*144 + [q_h(48) | k_h(48) | v_h(48)] (fused attention)
   Lin q;    // self-attention blocks: fused q|k|v (N = 1152); cross blocks: to_q (N = 384)
   Lin kv;   // cross blocks only: to_kv (N = 768)
   Lin out, fc1, fc2;
@@ -115,8 +117,9 @@ void place_lin(Lin& l, int N, int K, size_t& off) {
   l.b = off;
   off = align_up(off + (size_t)N * sizeof(float));
 }
-void place_block(Block& b, bool cross, size_t& off) {
+void place_block(Block& b, bool cross, size_t& off, bool time = false) {
   b.cross = cross;
+  if (time) place_lin(b.qkv_h, 3 * kC, kC, off);
   if (cross) {
     b.ctx_g = off; off = align_up(off + kC * sizeof(float));
     b.ctx_b = off; off = align_up(off + kC * sizeof(float));
@@ -142,7 +145,7 @@ const Layout& layout() {
     L.heads_w = off; off = align_up(off + 4 * kC * sizeof(float));
     L.heads_b = off; off = align_up(off + 4 * sizeof(float));
     for (int i = 0; i < kDepth; ++i) {
-      place_block(L.time[i], false, off);
+      place_block(L.time[i], false, off, /*time*/ true);
       place_block(L.vself[i], false, off);
       place_block(L.p2v[i], true, off);
       place_block(L.v2p[i], true, off);
@@ -304,15 +307,28 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
     {  // ---- time block over every token row (points + virtual): sequence = track (cotracker.py:494-495)
       const Block& b = L.time[i];
       RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
-      RUNC(-1, R.gemm(W.ln, b.q, Rall, Runner::to_f32(W.qkv, 3 * kC, false)));
-      AttnParams a{};
-      a.q = W.qkv; a.q_ld = 3 * kC; a.q_col = 0;
-      a.kv = W.qkv; a.kv_ld = 3 * kC; a.k_col = kC; a.v_col = 2 * kC;
-      a.out = W.att; a.out_ld = 2 * kC; a.lo_off = kC;
-      a.num_seq = N + kV; a.Lq = T; a.Lk = T;
-      a.q_seq_stride = T; a.q_tok_stride = 1; a.k_seq_stride = T; a.k_tok_stride = 1;
-      a.scale = scale;
-      RUNC(CAT_ATTN, run_attention(R, W, a, true));
+      if (g_opt[OPT_FUSE] == 1 && R.impl == 0 && g_opt_attn == 0 && qkv_time_attn_supported(T)) {
+        // q|k|v projection and the per-track T x T attention in ONE kernel: fp32 q|k|v never reaches HBM
+        ProfScope ps(R.s, CAT_GEMM, 2.0 * (double)Rall * 3 * kC * kC);
+        int rc = gemm_qkv_time_attn_launch(W.ln, reinterpret_cast<const __nv_bfloat16*>(pk + b.qkv_h.w),
+                                           reinterpret_cast<const float*>(pk + b.qkv_h.b), Rall, kC, T, W.att, 2 * kC,
+                                           kC, scale, num_sms(), R.s, &R.gerr);
+        if (rc != 0) {
+          snprintf(g_err, sizeof(g_err), "fused qkv + time attention failed: %s (%s)",
+                   cudaGetErrorString((cudaError_t)rc), R.gerr ? R.gerr : "");
+          return CT3_ECUDA;
+        }
+      } else {
+        RUNC(-1, R.gemm(W.ln, b.q, Rall, Runner::to_f32(W.qkv, 3 * kC, false)));
+        AttnParams a{};
+        a.q = W.qkv; a.q_ld = 3 * kC; a.q_col = 0;
+        a.kv = W.qkv; a.kv_ld = 3 * kC; a.k_col = kC; a.v_col = 2 * kC;
+        a.out = W.att; a.out_ld = 2 * kC; a.lo_off = kC;
+        a.num_seq = N + kV; a.Lq = T; a.Lk = T;
+        a.q_seq_stride = T; a.q_tok_stride = 1; a.k_seq_stride = T; a.k_tok_stride = 1;
+        a.scale = scale;
+        RUNC(CAT_ATTN, run_attention(R, W, a, true));
+      }
       RUNC(-1, R.gemm(W.att, b.out, Rall, Runner::to_f32(W.tokens, kC, true)));
       if (int rc = mlp_half(R, W, b, 0, Rall)) return rc;
     }
@@ -469,6 +485,14 @@ int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t 
     cudaError_t e;
     if ((e = put_lin(b.q, t[k], t[k + 1], kC, 0, 0)) != cudaSuccess) return e;            // to_q  -> rows [0,384)
     if ((e = put_lin(b.q, t[k + 2], t[k + 3], 2 * kC, kC, 0)) != cudaSuccess) return e;   // to_kv -> rows [384,1152)
+    if (b.qkv_h.N != 0) {   // per-head regrouping for the fused projection + time attention kernel
+      for (int h = 0; h < kHeads; ++h) {
+        const size_t wo = (size_t)h * kDh * kC;
+        if ((e = put_lin(b.qkv_h, t[k] + wo, t[k + 1] + h * kDh, kDh, h * 3 * kDh, 0)) != cudaSuccess) return e;                         // q_h
+        if ((e = put_lin(b.qkv_h, t[k + 2] + wo, t[k + 3] + h * kDh, kDh, h * 3 * kDh + kDh, 0)) != cudaSuccess) return e;               // k_h
+        if ((e = put_lin(b.qkv_h, t[k + 2] + (size_t)kC * kC + wo, t[k + 3] + kC + h * kDh, kDh, h * 3 * kDh + 2 * kDh, 0)) != cudaSuccess) return e;   // v_h
+      }
+    }
     if ((e = put_lin(b.out, t[k + 4], t[k + 5], kC, 0, 0)) != cudaSuccess) return e;
     if ((e = put_lin(b.fc1, t[k + 6], t[k + 7], kMlpHid, 0, 0)) != cudaSuccess) return e;
     if ((e = put_lin(b.fc2, t[k + 8], t[k + 9], kC, 0, 0)) != cudaSuccess) return e;

@@ -408,6 +408,240 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused  q|k|v projection + per-track time attention  (Attention.forward inside the time AttnBlock,
+// blocks.py:379-398, 426-432; cotracker.py:494-495):
+//     att[row, h*48 .. h*48+47] = softmax( q_h k_h^T * 48^-1/2 ) v_h      over the T frames of the row's track.
+// GEMM: X = LN(tokens) [M, 768 split] x Wqkv^T, the 1152 weight rows regrouped per head as [q_h(48) | k_h(48) | v_h(48)],
+// so one 128 x 144 output tile holds everything head h needs for the tracks of a row tile.  Token rows are
+// track-major (row = n*T + t): a tile starts at row mt*R with R = floor(128 / T) * T, i.e. it owns whole tracks
+// (the MMA still multiplies 128 rows; the rows past R belong to the next tile and are ignored).
+// cta_group::2 pairs as in gemm_split3_pair_kernel (256-row MMA, each CTA loads its 128 rows of X and 72 of the 144
+// weight rows).  Epilogue, per CTA on its own 128 rows: 8 warps = 2 groups x 4 TMEM lane quarters;
+//   group 1     : tcgen05.ld the k and v columns, + bias, -> shared [row][k 48 | v 48] fp32
+//   group 0     : tcgen05.ld the q columns (+ bias) into registers, then -- after a named barrier -- exact fp32
+//                 online-softmax attention of its row against the T key rows of its track in shared memory, and
+//                 writes the 48 outputs as split bf16 straight into the out-projection's operand buffer.
+// The fp32 q|k|v tensor (4.6 KB per token) never reaches HBM and the separate attention launch disappears.
+namespace qa {
+constexpr int BNQ = 144;                               // q|k|v of one head
+constexpr int TILE_BQ = (BNQ / 2) * BK * 2;            // 9216 B: this CTA's 72 weight rows, one plane
+constexpr int STAGE = 2 * TILE_A + 2 * TILE_BQ;        // 51200 B
+constexpr int NSTAGE = 3;
+constexpr int KV_LD = 100;                             // floats per row of the K/V buffer (96 + 4: conflict-free float4)
+constexpr int OFF_KV = NSTAGE * STAGE;                 // 153600
+constexpr int OFF_BARQ = OFF_KV + BM * KV_LD * 4;      // + 51200
+constexpr int SMEM = OFF_BARQ + 256 + 1024;
+constexpr int EPIW = 8;
+constexpr int NTHREADS = (2 + EPIW) * 32;              // 320 threads (10 warps): up to 168 registers per thread
+constexpr int ACC_STRIDE = 256;                        // TMEM columns between the two accumulators
+static_assert(SMEM <= 232448, "shared memory budget");
+}  // namespace qa
+
+__global__ void __launch_bounds__(qa::NTHREADS, 1)
+gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int M,
+                          int Kpad, int T, int R, float scale_log2e, GemmEpilogue epi) {
+  using namespace qa;
+  constexpr uint32_t TX_BYTES = 2u * (2u * TILE_A + 2u * TILE_BQ);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BARQ);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tfull_bar = empty_bar + NSTAGE;
+  uint64_t* tempty_bar = tfull_bar + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC);
+  float* kvs = reinterpret_cast<float*>(smem + OFF_KV);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * EPIW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_mt = (M + R - 1) / R;
+  const int num_mp = (num_mt + 1) / 2;
+  const int num_tiles = num_mp * kHeads;       // consecutive tiles = the 8 heads of one row-tile pair (X stays in L2)
+  const int num_kb = Kpad / BK;
+  const int first = blockIdx.x >> 1, step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first; tile < num_tiles; tile += step) {
+        const int mt = (tile / kHeads) * 2 + (int)rank, h = tile % kHeads;
+        const int wrow = h * BNQ + (int)rank * (BNQ / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], TX_BYTES);
+          uint8_t* s = smem + stage * STAGE;
+          tma_load_2d_2sm(s, &tmX, kb * BK, mt * R, &full_bar[stage]);
+          tma_load_2d_2sm(s + TILE_A, &tmX, Kpad + kb * BK, mt * R, &full_bar[stage]);
+          tma_load_2d_2sm(s + 2 * TILE_A, &tmW, kb * BK, wrow, &full_bar[stage]);
+          tma_load_2d_2sm(s + 2 * TILE_A + TILE_BQ, &tmW, Kpad + kb * BK, wrow, &full_bar[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BNQ);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = first; tile < num_tiles; tile += step) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_STRIDE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t s = smem_u32(smem + stage * STAGE);
+          const uint32_t a_hi = s, a_lo = s + TILE_A, b_hi = s + 2 * TILE_A, b_lo = b_hi + TILE_BQ;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint32_t koff = kk * 32;
+            const uint64_t dah = umma_desc_sw128(a_hi + koff), dbh = umma_desc_sw128(b_hi + koff);
+            umma_bf16_2sm(d_tmem, umma_desc_sw128(a_lo + koff), dbh, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, 1u);
+            umma_bf16_2sm(d_tmem, dah, dbh, idesc, 1u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;             // 0: q + attention, 1: k and v -> shared memory
+    const int r = quarter * 32 + lane;             // row of the tile = TMEM lane
+    const int tracks = R / T;
+    const int jtrack = min(r / T, tracks - 1);     // rows past R are computed on a clamped track and never stored
+    const float* kbase = kvs + (int64_t)jtrack * T * KV_LD;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first; tile < num_tiles; tile += step) {
+      const int mt = (tile / kHeads) * 2 + (int)rank, h = tile % kHeads;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      float x[kDh];
+      // part 0 = q (group 0) or k (group 1); part 1 = v (group 1 only)
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        if (part == 1 && group == 0) break;
+        const int col0 = (group == 0) ? 0 : kDh * (1 + part);
+#pragma unroll
+        for (int c = 0; c < kDh / 16; ++c) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)(col0 + 16 * c), v);
+          const float4* b4 = reinterpret_cast<const float4*>(epi.bias + h * BNQ + col0 + 16 * c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = __ldg(b4 + i);
+            x[16 * c + 4 * i + 0] = v[4 * i + 0] + b.x; x[16 * c + 4 * i + 1] = v[4 * i + 1] + b.y;
+            x[16 * c + 4 * i + 2] = v[4 * i + 2] + b.z; x[16 * c + 4 * i + 3] = v[4 * i + 3] + b.w;
+          }
+        }
+        if (group != 0) {
+          float4* dst = reinterpret_cast<float4*>(kvs + r * KV_LD + part * kDh);
+#pragma unroll
+          for (int i = 0; i < kDh / 4; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // accumulator drained (leader's barrier)
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // K/V of this tile are in shared memory
+      if (group == 0) {
+        float m = -INFINITY, l = 0.f;
+        float o[kDh];
+#pragma unroll
+        for (int i = 0; i < kDh; ++i) o[i] = 0.f;
+        for (int t0 = 0; t0 < T; t0 += 8) {
+          float sc[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sc[i] = 0.f;
+#pragma unroll
+          for (int d4 = 0; d4 < kDh / 4; ++d4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 kk = *reinterpret_cast<const float4*>(kbase + min(t0 + i, T - 1) * KV_LD + 4 * d4);
+              sc[i] = fmaf(x[4 * d4 + 0], kk.x, sc[i]);
+              sc[i] = fmaf(x[4 * d4 + 1], kk.y, sc[i]);
+              sc[i] = fmaf(x[4 * d4 + 2], kk.z, sc[i]);
+              sc[i] = fmaf(x[4 * d4 + 3], kk.w, sc[i]);
+            }
+          }
+          float mnew = m;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sc[i] = (t0 + i < T) ? sc[i] * scale_log2e : -INFINITY;
+            mnew = fmaxf(mnew, sc[i]);
+          }
+          const float corr = exp2f(m - mnew);          // exp2(-inf) = 0 on the first chunk
+          l *= corr;
+#pragma unroll
+          for (int i = 0; i < kDh; ++i) o[i] *= corr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pi = exp2f(sc[i] - mnew);      // 0 for the masked tail
+            l += pi;
+            const float* vr = kbase + min(t0 + i, T - 1) * KV_LD + kDh;
+#pragma unroll
+            for (int d4 = 0; d4 < kDh / 4; ++d4) {
+              const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * d4);
+              o[4 * d4 + 0] = fmaf(pi, vv.x, o[4 * d4 + 0]);
+              o[4 * d4 + 1] = fmaf(pi, vv.y, o[4 * d4 + 1]);
+              o[4 * d4 + 2] = fmaf(pi, vv.z, o[4 * d4 + 2]);
+              o[4 * d4 + 3] = fmaf(pi, vv.w, o[4 * d4 + 3]);
+            }
+          }
+          m = mnew;
+        }
+        const int64_t grow = (int64_t)mt * R + r;
+        if (r < R && grow < M) {
+          const float inv = 1.0f / l;
+          uint4* ph = reinterpret_cast<uint4*>(epi.out_split + grow * epi.ld_split + h * kDh);
+          uint4* pl = reinterpret_cast<uint4*>(epi.out_split + grow * epi.ld_split + epi.lo_off + h * kDh);
+#pragma unroll
+          for (int i = 0; i < kDh / 8; ++i) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split2(o[8 * i + 2 * j] * inv, o[8 * i + 2 * j + 1] * inv, hw[j], lw[j]);
+            ph[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            pl[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // K/V consumed: the next tile may overwrite the buffer
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // SIMT verification kernel: 64x64 tile, 256 threads, each 4x4 outputs; fp32 FMA on hi+lo.
 __device__ __forceinline__ void epilogue_store1(const GemmEpilogue& e, int N, int row, int col, float v) {
   if (e.bias) v += e.bias[col];
@@ -559,6 +793,60 @@ cudaError_t launch_tc(const GemmProblem& p, const CUtensorMap& tmX, const CUtens
 }
 
 }  // namespace
+
+bool qkv_time_attn_supported(int T) { return T >= 1 && T <= BM; }
+
+int gemm_qkv_time_attn_launch(const __nv_bfloat16* x_split, const __nv_bfloat16* w_heads, const float* bias_heads,
+                              int M, int Kpad, int T, __nv_bfloat16* att_split, int64_t ld_split, int lo_off,
+                              float scale, int num_sms, cudaStream_t stream, const char** err) {
+  *err = nullptr;
+  if (M <= 0 || Kpad <= 0 || (Kpad % BK) != 0 || !qkv_time_attn_supported(T) || (M % T) != 0) {
+    *err = "qkv_time_attn: need M > 0, M % T == 0, 1 <= T <= 128, Kpad % 64 == 0";
+    return (int)cudaErrorInvalidValue;
+  }
+  if (((reinterpret_cast<uintptr_t>(x_split) | reinterpret_cast<uintptr_t>(w_heads) |
+        reinterpret_cast<uintptr_t>(att_split)) & 15) || (ld_split % 8) != 0 || (lo_off % 8) != 0) {
+    *err = "qkv_time_attn: operands must be 16-byte aligned";
+    return (int)cudaErrorInvalidValue;
+  }
+  const int R = (BM / T) * T;
+  CUtensorMap tmX, tmW;
+  if (!make_tmap(&tmX, x_split, (uint64_t)M, 2ull * Kpad) ||
+      !make_tmap(&tmW, w_heads, (uint64_t)(kHeads * qa::BNQ), 2ull * Kpad, (uint32_t)(qa::BNQ / 2))) {
+    *err = "qkv_time_attn: cuTensorMapEncodeTiled failed";
+    return (int)cudaErrorInvalidValue;
+  }
+  static DeviceOnce attr;
+  cudaError_t e = once_per_device(attr, [&] {
+    return cudaFuncSetAttribute(gemm_qkv_time_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qa::SMEM);
+  });
+  if (e != cudaSuccess) { *err = "qkv_time_attn: cudaFuncSetAttribute failed"; return (int)e; }
+  const int num_mt = (M + R - 1) / R;
+  const int groups = ((num_mt + 1) / 2) * kHeads;
+  int pairs = num_sms / 2;
+  if (pairs > groups) pairs = groups;
+  GemmEpilogue epi;
+  epi.bias = bias_heads;
+  epi.out_split = att_split;
+  epi.ld_split = ld_split;
+  epi.lo_off = lo_off;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(qa::NTHREADS);
+  cfg.dynamicSmemBytes = qa::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gemm_qkv_time_attn_kernel, tmX, tmW, M, Kpad, T, R,
+                         scale * 1.44269504088896340736f, epi);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}
 
 int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream, const char** err) {
   *err = nullptr;

@@ -49,4 +49,13 @@ bool encode_tensor_map(CUtensorMap* m, CUtensorMapDataType dtype, int rank, cons
 // 0 = tcgen05 path, 1 = SIMT verification path.  Returns cudaError_t as int (0 = ok).
 int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream, const char** err);
 
+// Fused q|k|v projection + per-track time attention (gemm.cu, gemm_qkv_time_attn_kernel).
+//   x_split [M, 2*Kpad] (LayerNorm output, rows track-major n*T + t, M % T == 0), w_heads [8*144, 2*Kpad] with the
+//   rows of head h = [q_h | k_h | v_h], bias_heads [8*144] likewise; att_split[row*ld_split + h*48 + c] (hi) and
+//   + lo_off (lo) = softmax(q k^T scale) v.   T <= 128.
+bool qkv_time_attn_supported(int T);
+int gemm_qkv_time_attn_launch(const __nv_bfloat16* x_split, const __nv_bfloat16* w_heads, const float* bias_heads,
+                              int M, int Kpad, int T, __nv_bfloat16* att_split, int64_t ld_split, int lo_off,
+                              float scale, int num_sms, cudaStream_t stream, const char** err);
+
 }  // namespace ct3

@@ -79,8 +79,15 @@ def test_evaluation_predictor_matches_reference_golden(single_point):
     assert float((tracks.cpu() - wt).abs().max()) < 1e-3
     assert float((vis.cpu() - wv).abs().max()) < 1e-3
     q = queries[0].numpy()[None][..., [0, 2, 1]]                                     # (t, y, x)
-    occ_w = (wv[0].numpy().T < 0.6)[None]
-    occ_g = (vis[0].cpu().numpy().T < 0.6)[None]
+    # random-init weights give visibility*confidence far below the usual 0.6 cut: threshold in the widest gap around
+    # the median of the reference's values, so both classes are populated and no value sits on the threshold
+    vals = np.sort(wv.numpy().ravel())
+    mid = vals[len(vals) // 4: 3 * len(vals) // 4 + 1]
+    i = int(np.argmax(np.diff(mid)))
+    thr = 0.5 * (mid[i] + mid[i + 1])
+    occ_w = (wv[0].numpy().T < thr)[None]
+    occ_g = (vis[0].cpu().numpy().T < thr)[None]
+    assert occ_w.any() and not occ_w.all()
     tw = wt[0].permute(1, 0, 2).numpy()[None].astype(np.float64)
     tg = tracks[0].cpu().permute(1, 0, 2).numpy()[None].astype(np.float64)
     m = tapvid_metrics(q, occ_w, tw, occ_g, tg, "first")

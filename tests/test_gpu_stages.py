@@ -178,7 +178,9 @@ def test_corr_sample_precision_modes(eng, corr, fc1, tol, T, N, H4, W4):
     eng.set_option("prec.corr", corr)
     eng.set_option("prec.fc1", fc1)
     try:
-        assert eng.precision_info(T, H4, W4) == (corr, fc1, 4 if fc1 == 3 else 2)
+        patch = min(H4, W4) // 8 >= 8    # coarsest level >= 8x8 texels: the correlate-then-interpolate kernel runs;
+        # otherwise the sample-then-correlate kernel computes split x split whatever the switches say
+        assert eng.precision_info(T, H4, W4) == ((corr, fc1, 4 if fc1 == 3 else 2) if patch else (3, 3, 4))
         got = eng.corr_sample(pyr, H4, W4, support.to(DEV), valid.to(DEV), coords.to(DEV)).cpu()
     finally:
         eng.set_option("prec.corr", c0)
@@ -234,6 +236,29 @@ def test_updateformer_attention_shapes(eng, attn, N, T):
     scale = float(want.abs().max())
     err = float((got - want).abs().max())
     assert err < 2e-4 * max(scale, 1.0), (attn, N, T, err, scale)
+
+
+@pytest.mark.parametrize("N,T", [(70, 6), (333, 16), (130, 40), (50, 48), (21, 100), (9, 128), (5, 129)])
+def test_fused_qkv_time_attention(eng, N, T):
+    """gemm_qkv_time_attn_kernel (projection + per-track attention in one kernel; tile = floor(128/T) whole tracks,
+    ragged last tile, T = 128 -> one track per tile; T = 129 falls back to the separate kernels) against the oracle
+    and against the unfused path (`fuse` = 0)."""
+    sd = _amplified_sd(seed=5, head_gain=100.0, vis_gain=100.0)
+    g = torch.Generator().manual_seed(N * 131 + T)
+    x = torch.randn(N, T, 1110, generator=g)
+    with torch.no_grad():
+        want = O.updateformer(sd, x[None])[0]
+    packed = eng.pack_weights(sd, DEV)
+    got = {}
+    for fuse in (1, 0):
+        eng.set_option("fuse", fuse)
+        try:
+            got[fuse] = eng.updateformer(packed, x.to(DEV)).cpu()
+        finally:
+            eng.set_option("fuse", 1)
+    scale = max(float(want.abs().max()), 1.0)
+    assert float((got[1] - want).abs().max()) < 2e-4 * scale, (N, T, float((got[1] - want).abs().max()), scale)
+    assert float((got[1] - got[0]).abs().max()) < 1e-4 * scale
 
 
 def test_corr_mlp_gelu_variant_is_erf(eng):
