@@ -20,10 +20,11 @@ thread_local char g_err[512] = "";
 // another thread's verification switches or profile records.
 struct OptDef { const char* name; int lo, hi; };
 enum { OPT_GEMM = 0, OPT_CORR, OPT_ATTN, OPT_PREC_CORR, OPT_PREC_FC1, OPT_FUSE, OPT_COUNT };
-constexpr int kDefPrecCorr = 3, kDefPrecFc1 = 3;
+constexpr int kDefPrecCorr = 2, kDefPrecFc1 = 3;   // chosen by measurement: profiles/r2_precision_sweep.txt
 constexpr OptDef kOptDefs[OPT_COUNT] = {
     {"gemm", 0, 1},   // 0 tcgen05, 1 SIMT verification
-    {"corr", 0, 2},   // 0 tcgen05 correlate-then-interpolate (corr_tc2.cu), 1 exact-fp32 SIMT, 2 corr_tc.cu
+    {"corr", 0, 3},   // 0 tcgen05 correlate-then-interpolate (corr_tc3.cu / corr_tc2.cu), 1 exact-fp32 SIMT, 2 corr_tc.cu,
+                      // 3 correlate-then-interpolate with corr_tc2.cu for every precision mode (A/B)
     {"attn", 0, 1},   // 0 tensor-core kernels, 1 exact-fp32 SIMT verification
     // tensor-core products per FLOP of a GEMM group: 3 = split x split (hi*hi + lo*hi + hi*lo),
     // 2 = fp16 activation plane x split fp16 weights, 1 = single fp16 product.  Only the correlation branch has the

@@ -1,0 +1,492 @@
+// corr_tc3.cu -- fused bilinear sampling + 4-D correlation, production kernel ("CorrBlock.sample" of the north star):
+//
+//   vol[(n,t,l)][(a*7+b)*49 + k] = < bilinear(F_l[t], cx/2^l + a-3, cy/2^l + b-3) , S_l[n, k, :] >
+//   (get_correlation_feat + einsum, cotracker3_online.py:130-143, cotracker3_offline.py:144-156)
+//
+// Correlate-then-interpolate like corr_tc2.cu (bilinear sampling is linear in the feature map, so the tensor cores
+// correlate the RAW 8x8 texel patch around the track with the 49 support vectors and the epilogue blends the 64 raw
+// correlations into the 49 sampled ones), but with the MMA TRANSPOSED: the support vectors are the M side and the
+// texels the N side, so a thread of the epilogue owns ONE support vector k and sees all 64 raw correlations of a
+// frame as TMEM columns.  Both blends (x, then y) become plain FMAs on the thread's own registers with warp-uniform
+// weights: no shuffles, no exchange of texel rows between lanes -- corr_tc2.cu's epilogue (98 + 52 shuffles and a
+// shared-memory y-blend per tile) was what bounded that kernel (profiles/r2_corr_analysis.txt).
+//
+//   pyramid  : ONE fp16 plane per level [T][H][W][128] (made once per update-loop call); texels are rounded to fp16
+//              (2^-12 relative), the support vectors are exact to a split fp16 pair (prec.corr = 2)
+//   B tile   [128 texel rows x 128 ch] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, K-half) is
+//              ONE 4-D TMA box (64 ch x 8 x 8 x 1) landing in the 128B-swizzled K-major operand layout; ring of 6
+//              K-half slots (16 KiB), each freed as soon as its 4 MMAs retire
+//   A tile   [128 x 128 ch] : rows 0..63 hi plane / 64..127 lo plane of the 49 support vectors of (n,l) (rows 49..63
+//              of each half zero), built once per unit by 2 warps
+//   D        [128 x 128] fp32 in TMEM: lanes 0..63 = S_hi . F, lanes 64..127 = S_lo . F, columns = texels; ONE
+//              tcgen05.mma (M=128, N=128) per k16 step, 4 accumulators
+//   epilogue : 2 groups x 4 warps alternate tiles; thread = (part hi|lo, k).  Per frame: 4 x tcgen05.ld (two texel
+//              rows each) -> x-blend -> y-blend -> 49 sampled correlations of this part.  A border clamp only turns
+//              the tap indices into a clamped SHIFT of the interior pattern (idx = clamp(a + d, 0, 7), d uniform per
+//              frame and axis), so every case -- interior, any border, far outside -- runs the same register code
+//              through a warp-uniform switch on d; the per-sample weights (exactly tap_pair() of corr_tc2.cu,
+//              canonicalised to the shift pattern; tests/test_host_logic.py brute-forces that this always works)
+//              are computed once per tile by the otherwise idle lanes of the TMA warp.
+//              The hi and lo parts of a support vector sit in different warps: each part hands HALF of its 49
+//              values to the other through shared memory and finalises the other half (add, convert, write the
+//              row image), so all four warps do the same work.  Volume rows leave as bulk shared->global copies.
+// Warps: 0 TMA issuer (+ tap tables), 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace ct3 {
+namespace {
+
+constexpr int TMA_WARP = 0;
+constexpr int MMA_WARP = 1;
+constexpr int SB_WARP0 = 2;
+constexpr int EPI_WARP0 = 4;              // warps 4..7 group 0, 8..11 group 1; (warp & 3) = TMEM lane quarter
+constexpr int THREADS = 12 * 32;
+constexpr int NSLOT = 6;                  // texel ring: slots of one K-half (64 channels) of a 2-frame tile
+constexpr int A_SLOT = 16384;             // [128 texel rows x 128 B] fp16
+constexpr int S_HALF = 16384;             // one K-half of S: [hi rows 0..63 | lo rows 64..127] x 128 B
+constexpr int S_BYTES = 2 * S_HALF;
+constexpr int NACC = 4;
+constexpr uint32_t TMEM_COLS = NACC * 128;
+constexpr int NPARAM = 8;                 // tap-table ring (a tile's slot is rewritten only after its epilogue read it)
+constexpr int PRM_WORDS = 64;             // per tile: [frame 2][axis 2]{u[7], w[7]} = 56 floats, d[2][2] ints, flag
+constexpr int X_GROUP = 2 * kP * 64 * 4;  // exchange buffer per group: [frame 2][i 49][k 64] fp32 = 25088 B
+constexpr int ROW_BYTES_SPLIT = 2 * kVolPad * 2;   // 9728
+constexpr int ROW_BYTES_H16 = kVolPad * 2;         // 4864
+constexpr int IMG_GROUP = 2 * ROW_BYTES_SPLIT;
+constexpr int OFF_A = 0;
+constexpr int OFF_S = OFF_A + NSLOT * A_SLOT;
+constexpr int OFF_X = OFF_S + S_BYTES;
+constexpr int OFF_IMG = OFF_X + 2 * X_GROUP;
+constexpr int OFF_PARAM = OFF_IMG + 2 * IMG_GROUP;
+constexpr int OFF_BAR = OFF_PARAM + NPARAM * PRM_WORDS * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+struct Corr3Args {
+  PyramidLayout lay;
+  const float* support;        // [4][49, N, 128]
+  const uint8_t* track_valid;  // [N] or null
+  const float* coords;         // [T, N, 2]
+  int T, N;
+  uint16_t* vol;               // [N*T*4, 2*kVolPad] split bf16, or [N*T*4, kVolPad] fp16 (V16)
+};
+struct Corr3Maps {
+  CUtensorMap m[kL];           // per level: fp16 dims (128, W, H, T), box (64, 8, 8, 1), 128B swizzle
+};
+
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+__host__ __device__ constexpr int clamp07(int v) { return v < 0 ? 0 : (v > 7 ? 7 : v); }
+
+// origin of the 8-wide box holding every tap of the 7 border-clamped samples around c (size >= 8), and the shift of
+// the tap pattern relative to the interior one (0 = interior)
+__device__ __forceinline__ void box_origin8(float c, int size, int& origin, int& d) {
+  const float cc = fminf(fmaxf(c, -16.f), (float)size + 16.f);
+  const int base = (int)floorf(cc) - kR;
+  origin = max(0, min(base, size - 8));
+  d = max(-7, min(base - origin, 7));
+}
+
+// one border-clamped sample coordinate (exactly grid_sample(align_corners=True, padding_mode="border")) expressed in
+// the shift pattern: value = u * box[clamp07(a + d)] + w * box[clamp07(a + d + 1)].  Returns false if the sample does
+// not fit the pattern (never happens: brute-forced in tests/test_host_logic.py).
+__device__ __forceinline__ bool tap_weights(float c, int a, int size, int origin, int d, float& u, float& w) {
+  const float x = fminf(fmaxf(c + (float)(a - kR), 0.f), (float)(size - 1));
+  const float xf = floorf(x);
+  const int x0 = (int)xf;
+  const float fr = x - xf;
+  const int s0 = min(max(x0 - origin, 0), 7);
+  const int s1 = (fr > 0.f) ? min(max(min(x0 + 1, size - 1) - origin, 0), 7) : s0;
+  const int i0 = clamp07(a + d), i1 = clamp07(a + d + 1);
+  if (s0 == i0 && (fr == 0.f || s1 == i1)) { u = 1.f - fr; w = fr; return true; }
+  if (fr == 0.f && s0 == i1) { u = 0.f; w = 1.f; return true; }   // c + offset rounded up to the next integer in fp32
+  u = 0.f; w = 0.f;
+  return false;
+}
+
+// hx[a] = u[a] * row[clamp07(a + D)] + w[a] * row[clamp07(a + D + 1)]
+template <int D>
+__device__ __forceinline__ void xblend_row(const float* row, const float (&u)[7], const float (&w)[7], float* hx) {
+#pragma unroll
+  for (int a = 0; a < 7; ++a) hx[a] = u[a] * row[clamp07(a + D)] + w[a] * row[clamp07(a + D + 1)];
+}
+__device__ __forceinline__ void xblend_dispatch(int d, const float* row, const float (&u)[7], const float (&w)[7], float* hx) {
+  switch (d) {   // warp-uniform
+    case -7: xblend_row<-7>(row, u, w, hx); break;
+    case -6: xblend_row<-6>(row, u, w, hx); break;
+    case -5: xblend_row<-5>(row, u, w, hx); break;
+    case -4: xblend_row<-4>(row, u, w, hx); break;
+    case -3: xblend_row<-3>(row, u, w, hx); break;
+    case -2: xblend_row<-2>(row, u, w, hx); break;
+    case -1: xblend_row<-1>(row, u, w, hx); break;
+    case 0: xblend_row<0>(row, u, w, hx); break;
+    case 1: xblend_row<1>(row, u, w, hx); break;
+    case 2: xblend_row<2>(row, u, w, hx); break;
+    case 3: xblend_row<3>(row, u, w, hx); break;
+    case 4: xblend_row<4>(row, u, w, hx); break;
+    case 5: xblend_row<5>(row, u, w, hx); break;
+    case 6: xblend_row<6>(row, u, w, hx); break;
+    default: xblend_row<7>(row, u, w, hx); break;
+  }
+}
+// out[a*7 + b] = uy[b] * hx[clamp07(b + D)][a] + wy[b] * hx[clamp07(b + D + 1)][a]
+template <int D>
+__device__ __forceinline__ void yblend(const float (&hx)[8][7], const float (&u)[7], const float (&w)[7], float (&out)[kP]) {
+#pragma unroll
+  for (int b = 0; b < 7; ++b)
+#pragma unroll
+    for (int a = 0; a < 7; ++a) out[a * 7 + b] = u[b] * hx[clamp07(b + D)][a] + w[b] * hx[clamp07(b + D + 1)][a];
+}
+__device__ __forceinline__ void yblend_dispatch(int d, const float (&hx)[8][7], const float (&u)[7], const float (&w)[7],
+                                                float (&out)[kP]) {
+  switch (d) {
+    case -7: yblend<-7>(hx, u, w, out); break;
+    case -6: yblend<-6>(hx, u, w, out); break;
+    case -5: yblend<-5>(hx, u, w, out); break;
+    case -4: yblend<-4>(hx, u, w, out); break;
+    case -3: yblend<-3>(hx, u, w, out); break;
+    case -2: yblend<-2>(hx, u, w, out); break;
+    case -1: yblend<-1>(hx, u, w, out); break;
+    case 0: yblend<0>(hx, u, w, out); break;
+    case 1: yblend<1>(hx, u, w, out); break;
+    case 2: yblend<2>(hx, u, w, out); break;
+    case 3: yblend<3>(hx, u, w, out); break;
+    case 4: yblend<4>(hx, u, w, out); break;
+    case 5: yblend<5>(hx, u, w, out); break;
+    case 6: yblend<6>(hx, u, w, out); break;
+    default: yblend<7>(hx, u, w, out); break;
+  }
+}
+
+// Epilogue of one 2-frame tile for one thread = (PART hi|lo of support vector k).  PART p keeps outputs
+// i in [KEEP0, KEEP1) of each frame and hands the rest to its partner (same k, other part) through `xbuf`.
+template <int PART, bool V16>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int acc, int q, int lane, int grp, int nf,
+                                              const float* prm, float* xbuf, uint16_t* img, uint64_t* d_empty_bar,
+                                              uint16_t* vrow) {
+  constexpr int ROW_BYTES = V16 ? ROW_BYTES_H16 : ROW_BYTES_SPLIT;
+  constexpr int KEEP0 = PART == 0 ? 0 : 25, KEEP1 = PART == 0 ? 25 : kP, NKEEP = KEEP1 - KEEP0;
+  const int k = (q & 1) * 32 + lane;
+  const bool live = k < kP;
+  const int r128 = q * 32 + lane;
+  const int bar_id = 1 + 2 * grp;
+  const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+  const int* iprm = reinterpret_cast<const int*>(prm) + 56;
+  if (iprm[4] == 0) asm volatile("trap;");   // a sample outside the shift pattern: impossible (see file header)
+  float keep[2][NKEEP];
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    if (f < nf) {
+      float hx[8][7];
+      {
+        float ux[7], wx[7];
+#pragma unroll
+        for (int a = 0; a < 7; ++a) { ux[a] = prm[(f * 2 + 0) * 14 + a]; wx[a] = prm[(f * 2 + 0) * 14 + 7 + a]; }
+        const int dx = iprm[2 * f];
+#pragma unroll
+        for (int y2 = 0; y2 < 4; ++y2) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)(f * 64 + y2 * 16), v);
+          xblend_dispatch(dx, v, ux, wx, hx[2 * y2]);
+          xblend_dispatch(dx, v + 8, ux, wx, hx[2 * y2 + 1]);
+        }
+      }
+      float out[kP];
+      {
+        float uy[7], wy[7];
+#pragma unroll
+        for (int b = 0; b < 7; ++b) { uy[b] = prm[(f * 2 + 1) * 14 + b]; wy[b] = prm[(f * 2 + 1) * 14 + 7 + b]; }
+        yblend_dispatch(iprm[2 * f + 1], hx, uy, wy, out);
+      }
+      if (live) {   // the partner's half: xbuf[f][i][k]
+#pragma unroll
+        for (int i = 0; i < kP; ++i)
+          if (i < KEEP0 || i >= KEEP1) xbuf[(f * kP + i) * 64 + k] = out[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NKEEP; ++i) keep[f][i] = out[KEEP0 + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NKEEP; ++i) keep[f][i] = 0.f;
+    }
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(d_empty_bar);            // accumulator fully read
+  if (r128 == 0) bulk_wait_read0();                   // previous tile's row images have left shared memory
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // exchange complete, images reusable
+  if (live) {
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      if (f < nf) {
+#pragma unroll
+        for (int i = 0; i < NKEEP; ++i) {
+          const float v = keep[f][i] + xbuf[(f * kP + KEEP0 + i) * 64 + k];
+          const int e = (KEEP0 + i) * kP + k;
+          if (V16) {
+            img[f * kVolPad + e] = __half_as_ushort(__float2half_rn(v));
+          } else {
+            const bf16pair sp = split_bf16(v);
+            img[f * 2 * kVolPad + e] = __bfloat16_as_ushort(sp.hi);
+            img[f * 2 * kVolPad + kVolPad + e] = __bfloat16_as_ushort(sp.lo);
+          }
+        }
+      }
+    }
+  }
+  fence_proxy_async_smem();                   // image writes -> visible to the bulk-copy (async proxy) reads
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id + 1) : "memory");
+  if (r128 == 0) {
+#pragma unroll
+    for (int t2 = 0; t2 < 2; ++t2)
+      if (t2 < nf) bulk_store_s2g(vrow + (int64_t)t2 * kL * (ROW_BYTES / 2), reinterpret_cast<uint8_t*>(img) + t2 * ROW_BYTES, ROW_BYTES);
+    bulk_commit();
+  }
+}
+
+template <bool V16>
+__global__ void __launch_bounds__(THREADS, 1)
+corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__ Corr3Maps maps, int num_units) {
+  constexpr int ROW_BYTES = V16 ? ROW_BYTES_H16 : ROW_BYTES_SPLIT;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* a_full = bars;                          // [NSLOT] TMA -> MMA         (count 1 + tx bytes)
+  uint64_t* a_empty = bars + NSLOT;                 // [NSLOT] MMA -> TMA         (tcgen05.commit)
+  uint64_t* d_full = bars + 2 * NSLOT;              // [NACC] MMA -> epilogue group  (tcgen05.commit)
+  uint64_t* d_empty = bars + 2 * NSLOT + NACC;      // [NACC] epilogue group -> MMA  (count 4)
+  uint64_t* s_full = bars + 2 * NSLOT + 2 * NACC;       // builders -> MMA, per unit  (count 2)
+  uint64_t* s_empty = bars + 2 * NSLOT + 2 * NACC + 1;  // MMA -> builders, per unit  (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * NACC + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_unit = (g.T + 1) / 2;
+
+  // one-time: zero S (rows 49..63 of each half stay zero forever) and the two row images (K padding stays zero)
+  for (int i = threadIdx.x; i < S_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_S)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * IMG_GROUP / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_IMG)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < NACC; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 4);
+    }
+    mbar_init(s_full, 2);
+    mbar_init(s_empty, 1);
+    fence_barrier_init();
+    for (int l = 0; l < kL; ++l) tma_prefetch_desc(&maps.m[l]);
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TMA_WARP) {
+    // ================================================================== TMA issuer + tap tables (whole warp)
+    uint32_t it = 0, hc = 0;   // tile / K-half slot counters
+    // lane -> (frame, axis, a) of the tap this lane evaluates for every tile
+    const int pf = lane / 14, pax = (lane % 14) / 7, pa = lane % 7;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int n = u / kL, l = u % kL;
+      const int H = g.lay.h[l], W = g.lay.w[l];
+      const float inv = 1.0f / (float)(1 << l);
+      for (int t0 = 0; t0 < g.T; t0 += 32) {
+        const int tl = min(t0 + lane, g.T - 1);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(g.coords + ((int64_t)tl * g.N + n) * 2));
+        const int cnt = min(32, g.T - t0);
+        for (int k = 0; k < cnt; k += 2, ++it) {
+          const int k1 = min(k + 1, 31);
+          const float cx0 = __shfl_sync(0xffffffffu, c.x, k) * inv, cy0 = __shfl_sync(0xffffffffu, c.y, k) * inv;
+          const float cx1 = __shfl_sync(0xffffffffu, c.x, k1) * inv, cy1 = __shfl_sync(0xffffffffu, c.y, k1) * inv;
+          int bx0, by0, bx1, by1, dx0, dy0, dx1, dy1;
+          box_origin8(cx0, W, bx0, dx0);
+          box_origin8(cy0, H, by0, dy0);
+          box_origin8(cx1, W, bx1, dx1);
+          box_origin8(cy1, H, by1, dy1);
+          // the first K-half slot of this tile doubles as the "previous epilogue has read the table slot" gate:
+          // slot it % NPARAM was last used by tile it - 8, whose accumulator (and therefore its table) was consumed
+          // before accumulator it - 4 could be reissued (NACC = 4 < NPARAM)
+          mbar_wait_spin(&a_empty[hc % NSLOT], ((hc / NSLOT) & 1u) ^ 1u);
+          {
+            float* prm = reinterpret_cast<float*>(smem + OFF_PARAM) + (it % NPARAM) * PRM_WORDS;
+            bool ok = true;
+            if (lane < 28) {
+              const float cc = pf ? (pax ? cy1 : cx1) : (pax ? cy0 : cx0);
+              const int size = pax ? H : W;
+              const int org = pf ? (pax ? by1 : bx1) : (pax ? by0 : bx0);
+              const int dd = pf ? (pax ? dy1 : dx1) : (pax ? dy0 : dx0);
+              float uu, ww;
+              ok = tap_weights(cc, pa, size, org, dd, uu, ww);
+              prm[(pf * 2 + pax) * 14 + pa] = uu;
+              prm[(pf * 2 + pax) * 14 + 7 + pa] = ww;
+            }
+            const bool all_ok = __all_sync(0xffffffffu, ok);
+            if (lane == 0) {
+              int* ip = reinterpret_cast<int*>(prm) + 56;
+              ip[0] = dx0; ip[1] = dy0; ip[2] = dx1; ip[3] = dy1;
+              ip[4] = all_ok ? 1 : 0;
+            }
+          }
+          __syncwarp();   // table stores of all lanes precede the arrive below (-> a_full -> d_full -> epilogue)
+          if (elect_one()) {
+            const int nf = (k + 1 < cnt) ? 2 : 1;
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+              const uint32_t h = hc + kh;
+              const int sl = h % NSLOT;
+              if (kh == 1) mbar_wait_spin(&a_empty[sl], ((h / NSLOT) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&a_full[sl], (uint32_t)(nf * (A_SLOT / 2)));
+              uint8_t* dst = smem + OFF_A + sl * A_SLOT;
+              tma_load_4d(dst, &maps.m[l], kh * 64, bx0, by0, t0 + k, &a_full[sl]);
+              if (nf == 2) tma_load_4d(dst + 8192, &maps.m[l], kh * 64, bx1, by1, t0 + k + 1, &a_full[sl]);
+            }
+          }
+          hc += 2;        // every lane tracks the slot counter (the table gate above is a warp-wide wait)
+          __syncwarp();
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_16(128, 128, /*fp16*/ true);
+      uint32_t it = 0, ui = 0, hc = 0;
+      const uint32_t s_base = smem_u32(smem + OFF_S);
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+        mbar_wait_spin(s_full, ui & 1u);
+        for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
+          const int acc = it % NACC;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+#pragma unroll
+          for (int kh = 0; kh < 2; ++kh, ++hc) {
+            const int sl = hc % NSLOT;
+            mbar_wait_spin(&a_full[sl], (hc / NSLOT) & 1u);
+            if (kh == 0) mbar_wait_spin(&d_empty[acc], ((it / NACC) & 1u) ^ 1u);
+            tc_fence_after_sync();
+            const uint32_t f_base = smem_u32(smem + OFF_A + sl * A_SLOT);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // D[support row][texel] += [S_hi ; S_lo](128 x 16) * F(128 texels x 16)^T
+              const uint64_t ds = umma_desc_sw128(s_base + (uint32_t)(kh * S_HALF + j * 32));
+              const uint64_t df = umma_desc_sw128(f_base + j * 32);
+              umma_bf16(d_tmem, ds, df, idesc, (kh | j) != 0 ? 1u : 0u);
+            }
+            umma_commit(&a_empty[sl]);
+          }
+          umma_commit(&d_full[acc]);
+        }
+        umma_commit(s_empty);
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    // ================================================================== support builders (A operand, once per unit)
+    const int sb = warp - SB_WARP0;
+    const int atom = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;  // where this lane's 4 channels live
+    uint8_t* s_hi = smem + OFF_S;
+    uint32_t ui = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+      const int n = u / kL, l = u % kL;
+      const bool valid = g.track_valid == nullptr || g.track_valid[n] != 0;
+      float4 rows[25];
+#pragma unroll
+      for (int j = 0; j < 25; ++j) {
+        const int p = sb + 2 * j;
+        rows[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < kP && valid)
+          rows[j] = __ldg(reinterpret_cast<const float4*>(g.support + ((int64_t)l * kP * g.N + (int64_t)p * g.N + n) * kD) + lane);
+      }
+      if (ui > 0) mbar_wait(s_empty, (ui - 1) & 1u);   // MMAs of the previous unit have retired
+#pragma unroll
+      for (int j = 0; j < 25; ++j) {
+        const int p = sb + 2 * j;
+        if (p < kP) {
+          uint32_t h0, l0, h1, l1;
+          split2_h(rows[j].x, rows[j].y, h0, l0);
+          split2_h(rows[j].z, rows[j].w, h1, l1);
+          const uint32_t off = (uint32_t)(atom * S_HALF) + sw128(p, chunk) + (uint32_t)(half * 8);
+          *reinterpret_cast<uint2*>(s_hi + off) = make_uint2(h0, h1);          // rows 0..63 of the K-half: hi plane
+          *reinterpret_cast<uint2*>(s_hi + 8192 + off) = make_uint2(l0, l1);   // rows 64..127: lo plane
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full);
+    }
+  } else {
+    // ================================================================== epilogue
+    const int grp = (warp - EPI_WARP0) >> 2;   // tiles with (it & 1) == grp
+    const int q = warp & 3;                    // TMEM lane quarter; quarters 0,1 = S_hi rows, 2,3 = S_lo rows
+    float* xbuf = reinterpret_cast<float*>(smem + OFF_X + grp * X_GROUP);
+    uint16_t* img = reinterpret_cast<uint16_t*>(smem + OFF_IMG + grp * IMG_GROUP);
+    const float* prm_base = reinterpret_cast<const float*>(smem + OFF_PARAM);
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int n = u / kL, l = u % kL;
+      for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
+        if ((int)(it & 1u) != grp) continue;
+        const int acc = it % NACC;
+        mbar_wait(&d_full[acc], (it / NACC) & 1u);
+        tc_fence_after_sync();
+        const float* prm = prm_base + (it % NPARAM) * PRM_WORDS;
+        const int nf = (2 * tp + 1 < g.T) ? 2 : 1;
+        uint16_t* vrow = g.vol + (((int64_t)n * g.T + 2 * tp) * kL + l) * (ROW_BYTES / 2);
+        if (q < 2) epilogue_tile<0, V16>(tmem_base, acc, q, lane, grp, nf, prm, xbuf, img, &d_empty[acc], vrow);
+        else       epilogue_tile<1, V16>(tmem_base, acc, q, lane, grp, nf, prm, xbuf, img, &d_empty[acc], vrow);
+      }
+    }
+  }
+
+  if (warp >= EPI_WARP0 && (threadIdx.x & 127) == 0) bulk_wait0();   // outstanding volume-row copies
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <bool V16>
+cudaError_t launch_variant(const Corr3Args& g, const Corr3Maps& maps, int num_units, int num_sms, cudaStream_t s) {
+  static DeviceOnce attr;
+  cudaError_t e = once_per_device(attr, [&] {
+    return cudaFuncSetAttribute(corr_patch_t_kernel<V16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  if (e != cudaSuccess) return e;
+  const int grid = num_units < num_sms ? num_units : num_sms;
+  corr_patch_t_kernel<V16><<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_corr_patch_t(const __nv_bfloat16* pyr_half, int H4, int W4, const float* support,
+                                const uint8_t* track_valid, const float* coords, int T, int N,
+                                __nv_bfloat16* vol, int vol16, int num_sms, cudaStream_t s) {
+  Corr3Args g;
+  g.lay = pyramid_layout(T, H4, W4);
+  g.support = support;
+  g.track_valid = track_valid;
+  g.coords = coords;
+  g.T = T;
+  g.N = N;
+  g.vol = reinterpret_cast<uint16_t*>(vol);
+  Corr3Maps maps;
+  for (int l = 0; l < kL; ++l) {
+    const uint64_t W = (uint64_t)g.lay.w[l], H = (uint64_t)g.lay.h[l];
+    if (W < 8 || H < 8) return cudaErrorInvalidValue;
+    const uint64_t dims[4] = {(uint64_t)kD, W, H, (uint64_t)T};
+    const uint64_t strides[3] = {(uint64_t)kD * 2, W * kD * 2, H * W * kD * 2};
+    const uint32_t box[4] = {64, 8, 8, 1};
+    if (!encode_tensor_map(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pyr_half + 2 * g.lay.off[l], dims, strides,
+                           box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return cudaErrorInvalidValue;
+  }
+  const int num_units = N * kL;
+  return vol16 ? launch_variant<true>(g, maps, num_units, num_sms, s)
+               : launch_variant<false>(g, maps, num_units, num_sms, s);
+}
+
+}  // namespace ct3

@@ -31,8 +31,9 @@ cudaError_t launch_upsample_concat(const float* const src[4], const int c[4], co
 
 // ---- corr.cu : correlation sampling ---------------------------------------------------------------
 // vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level
-// impl: 0 tensor cores (corr_tc2.cu when pyr_split is given and every level is >= 8x8, else corr_tc.cu),
-//       1 exact-fp32 SIMT, 2 corr_tc.cu always
+// impl: 0 tensor cores (correlate-then-interpolate when pyr_split is given and every level is >= 8x8: corr_tc3.cu for
+//         mode 2, corr_tc2.cu for modes 3 / 1; else corr_tc.cu),
+//       1 exact-fp32 SIMT, 2 corr_tc.cu always, 3 like 0 but corr_tc2.cu for every mode (A/B of the two kernels)
 // mode / vol16 apply to the corr_tc2.cu path only (corr_uses_patch_kernel): products per correlation FLOP (3|2|1;
 // pyr_split must have been made with the same mode) and a single-fp16-plane volume [N*T*4, kVolPad] instead of the
 // split one; the other kernels always compute in fp32 / bf16x3 and write the split volume.
@@ -54,6 +55,12 @@ cudaError_t launch_split_pyramid(const float* pyr, int T, int H4, int W4, __nv_b
 cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4, const float* support,
                                  const uint8_t* track_valid, const float* coords, int T, int N,
                                  __nv_bfloat16* vol_split, int mode, int vol16, int num_sms, cudaStream_t s);
+
+// corr_tc3.cu: the production kernel -- same algorithm with the MMA transposed (supports = M side), one fp16 texel
+// plane (pyr_split made with mode 2), split-fp16 supports: the numerics of mode 2
+cudaError_t launch_corr_patch_t(const __nv_bfloat16* pyr_half, int H4, int W4, const float* support,
+                                const uint8_t* track_valid, const float* coords, int T, int N,
+                                __nv_bfloat16* vol, int vol16, int num_sms, cudaStream_t s);
 
 // ---- tokens.cu : elementwise / row-wise pieces of the transformer ---------------------------------
 cudaError_t launch_layernorm_split(const float* x, int rows, const float* gamma, const float* beta, float eps,

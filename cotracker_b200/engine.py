@@ -263,7 +263,7 @@ def corr_sample(pyr, H4, W4, support, track_valid, coords, scratch: bool = True)
     vol = torch.zeros(N * T * LEVELS, 2 * VOL_PAD, dtype=torch.bfloat16, device=coords.device)
     scr = torch.empty(pyr.numel() * 4, dtype=torch.uint8, device=coords.device) if scratch else None
     # a single fp16 plane [rows, 2432] when the correlate-then-interpolate kernel runs with prec.fc1 < 3
-    vb = precision_info(T, H4, W4)[2] if (scratch and get_option("corr") == 0) else 4
+    vb = precision_info(T, H4, W4)[2] if (scratch and get_option("corr") in (0, 3)) else 4
     with torch.cuda.device(coords.device):
         _check(lib().ct3_corr_sample(_ptr(pyr), H4, W4, _ptr(support), _ptr(track_valid), _ptr(coords), T, N, _ptr(vol),
                                      _ptr(scr), scr.numel() if scratch else 0, _stream(coords.device)),

@@ -132,8 +132,8 @@ def test_sample_support(eng):
 
 # impl 0: tensor-core product path (correlate-then-interpolate kernel when every level is >= 8x8, i.e. the
 # 64x64 / 64x72 / 96x128 cases; sample-then-correlate otherwise), 1: exact-fp32 SIMT cross-check,
-# 2: sample-then-correlate tensor-core kernel forced
-@pytest.mark.parametrize("impl", [0, 1, 2])
+# 2: sample-then-correlate tensor-core kernel forced, 3: correlate-then-interpolate with the previous kernel (corr_tc2.cu)
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("T,N,H4,W4", [(3, 16, 24, 32), (2, 9, 8, 8), (5, 33, 96, 128), (1, 5, 16, 24), (16, 300, 96, 128),
                                        (2, 40, 64, 64), (3, 150, 64, 72)])
 def test_corr_sample(eng, impl, T, N, H4, W4):
@@ -155,7 +155,9 @@ def test_corr_sample(eng, impl, T, N, H4, W4):
     for l in range(4):
         want = O.correlation_volume(want_pyr[l], support[l] * valid[None, :, None].float(), coords / 2 ** l)  # [T,N,2401]
         err = float((got[:, :, l].permute(1, 0, 2) - want).abs().max())
-        assert err < 5e-5, (impl, l, err)   # |corr| <= 1; grid_sample normalise/denormalise noise ~1e-5, bf16x3 ~1e-5
+        # |corr| <= 1; grid_sample normalise/denormalise noise ~1e-5, bf16x3 ~1e-5; the default precision of the
+        # correlate-then-interpolate kernels (prec.corr = 2) rounds the texels to fp16: + ~3e-5
+        assert err < (1.2e-4 if impl in (0, 3) else 5e-5), (impl, l, err)
     assert bool((got[dead] == 0).all())
 
 
