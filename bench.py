@@ -387,7 +387,7 @@ def main():
                              "the GEMM launches; products per FLOP: " + prec["products"] + "; peak = sustained cuBLAS "
                              "bf16 (" + pk["source"] + ")",
                      "ms_per_step": cat_ms["gemm"], "launches_per_step": cat_n["gemm"]},
-        "roofline_corr": {"kernel": "corr_patch_tc_kernel (corr_tc2.cu; fused sampling + 4-D correlation)",
+        "roofline_corr": {"kernel": "corr_patch_t_kernel (corr_tc3.cu; fused bilinear sampling + 4-D correlation)",
                           "bound": "hbm", "achieved": corr_gbs, "peak": pk["hbm"],
                           "unit": "GB/s", "frac": corr_gbs / pk["hbm"],
                           "traffic": traffic.get("corr_sample", {}).get("dram_bytes_per_step"),

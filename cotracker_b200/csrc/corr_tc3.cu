@@ -27,9 +27,10 @@
 //              through a warp-uniform switch on d; the per-sample weights (exactly tap_pair() of corr_tc2.cu,
 //              canonicalised to the shift pattern; tests/test_host_logic.py brute-forces that this always works)
 //              are computed once per tile by the otherwise idle lanes of the TMA warp.
-//              The hi and lo parts of a support vector sit in different warps: each part hands HALF of its 49
-//              values to the other through shared memory and finalises the other half (add, convert, write the
-//              row image), so all four warps do the same work.  Volume rows leave as bulk shared->global copies.
+//              The hi and lo parts of a support vector sit in different warps: for frame 0 the hi part hands its 49
+//              values to the lo part through shared memory, for frame 1 the other way round, and the receiver adds,
+//              converts and writes the row image -- all four warps do the same work.  The blend code exists once
+//              (58 KB of SASS: frame loop not unrolled).  Volume rows leave as bulk shared->global copies.
 // Warps: 0 TMA issuer (+ tap tables), 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -104,29 +105,32 @@ __device__ __forceinline__ bool tap_weights(float c, int a, int size, int origin
   return false;
 }
 
-// hx[a] = u[a] * row[clamp07(a + D)] + w[a] * row[clamp07(a + D + 1)]
+// hx[y][a] = u[a] * v[y*8 + clamp07(a + D)] + w[a] * v[y*8 + clamp07(a + D + 1)]   for the 8 texel rows of a frame
 template <int D>
-__device__ __forceinline__ void xblend_row(const float* row, const float (&u)[7], const float (&w)[7], float* hx) {
+__device__ __forceinline__ void xblend(const float (&v)[64], const float (&u)[7], const float (&w)[7], float (&hx)[8][7]) {
 #pragma unroll
-  for (int a = 0; a < 7; ++a) hx[a] = u[a] * row[clamp07(a + D)] + w[a] * row[clamp07(a + D + 1)];
+  for (int y = 0; y < 8; ++y)
+#pragma unroll
+    for (int a = 0; a < 7; ++a) hx[y][a] = u[a] * v[y * 8 + clamp07(a + D)] + w[a] * v[y * 8 + clamp07(a + D + 1)];
 }
-__device__ __forceinline__ void xblend_dispatch(int d, const float* row, const float (&u)[7], const float (&w)[7], float* hx) {
+__device__ __forceinline__ void xblend_dispatch(int d, const float (&v)[64], const float (&u)[7], const float (&w)[7],
+                                                float (&hx)[8][7]) {
   switch (d) {   // warp-uniform
-    case -7: xblend_row<-7>(row, u, w, hx); break;
-    case -6: xblend_row<-6>(row, u, w, hx); break;
-    case -5: xblend_row<-5>(row, u, w, hx); break;
-    case -4: xblend_row<-4>(row, u, w, hx); break;
-    case -3: xblend_row<-3>(row, u, w, hx); break;
-    case -2: xblend_row<-2>(row, u, w, hx); break;
-    case -1: xblend_row<-1>(row, u, w, hx); break;
-    case 0: xblend_row<0>(row, u, w, hx); break;
-    case 1: xblend_row<1>(row, u, w, hx); break;
-    case 2: xblend_row<2>(row, u, w, hx); break;
-    case 3: xblend_row<3>(row, u, w, hx); break;
-    case 4: xblend_row<4>(row, u, w, hx); break;
-    case 5: xblend_row<5>(row, u, w, hx); break;
-    case 6: xblend_row<6>(row, u, w, hx); break;
-    default: xblend_row<7>(row, u, w, hx); break;
+    case -7: xblend<-7>(v, u, w, hx); break;
+    case -6: xblend<-6>(v, u, w, hx); break;
+    case -5: xblend<-5>(v, u, w, hx); break;
+    case -4: xblend<-4>(v, u, w, hx); break;
+    case -3: xblend<-3>(v, u, w, hx); break;
+    case -2: xblend<-2>(v, u, w, hx); break;
+    case -1: xblend<-1>(v, u, w, hx); break;
+    case 0: xblend<0>(v, u, w, hx); break;
+    case 1: xblend<1>(v, u, w, hx); break;
+    case 2: xblend<2>(v, u, w, hx); break;
+    case 3: xblend<3>(v, u, w, hx); break;
+    case 4: xblend<4>(v, u, w, hx); break;
+    case 5: xblend<5>(v, u, w, hx); break;
+    case 6: xblend<6>(v, u, w, hx); break;
+    default: xblend<7>(v, u, w, hx); break;
   }
 }
 // out[a*7 + b] = uy[b] * hx[clamp07(b + D)][a] + wy[b] * hx[clamp07(b + D + 1)][a]
@@ -158,84 +162,85 @@ __device__ __forceinline__ void yblend_dispatch(int d, const float (&hx)[8][7], 
   }
 }
 
-// Epilogue of one 2-frame tile for one thread = (PART hi|lo of support vector k).  PART p keeps outputs
-// i in [KEEP0, KEEP1) of each frame and hands the rest to its partner (same k, other part) through `xbuf`.
-template <int PART, bool V16>
+// Epilogue of one 2-frame tile for one thread = (part hi|lo of support vector k).  The blend code exists ONCE (the
+// frame loop is not unrolled; a fully unrolled version is 290 KB of SASS and thrashes the instruction cache: measured
+// 10.7 ms per launch instead of ~1).  Per frame both parts blend their 49 values; then the part that equals the frame
+// index stores them to `xbuf` and the OTHER part adds its own, converts and writes the volume-row image -- so the lo
+// warps finalise frame 0 and the hi warps frame 1, and all four warps do the same work.
+template <bool V16>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int acc, int q, int lane, int grp, int nf,
                                               const float* prm, float* xbuf, uint16_t* img, uint64_t* d_empty_bar,
                                               uint16_t* vrow) {
   constexpr int ROW_BYTES = V16 ? ROW_BYTES_H16 : ROW_BYTES_SPLIT;
-  constexpr int KEEP0 = PART == 0 ? 0 : 25, KEEP1 = PART == 0 ? 25 : kP, NKEEP = KEEP1 - KEEP0;
+  const int part = q >> 1;                            // 0: S_hi rows (TMEM lanes 0..63), 1: S_lo rows
   const int k = (q & 1) * 32 + lane;
   const bool live = k < kP;
   const int r128 = q * 32 + lane;
-  const int bar_id = 1 + 2 * grp;
+  const int bar0 = 1 + 3 * grp;                       // named barriers of this group: frame 0, frame 1, tile end
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
   const int* iprm = reinterpret_cast<const int*>(prm) + 56;
   if (iprm[4] == 0) asm volatile("trap;");   // a sample outside the shift pattern: impossible (see file header)
-  float keep[2][NKEEP];
-#pragma unroll
+  if (r128 == 0) bulk_wait_read0();          // previous tile's row images have left shared memory
+#pragma unroll 1
   for (int f = 0; f < 2; ++f) {
+    float out[kP];
     if (f < nf) {
       float hx[8][7];
       {
+        float v[64];
+#pragma unroll
+        for (int y2 = 0; y2 < 4; ++y2) {
+          float t16[16];
+          tmem_ld16(tlane + (uint32_t)(f * 64 + y2 * 16), t16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[y2 * 16 + j] = t16[j];
+        }
         float ux[7], wx[7];
 #pragma unroll
         for (int a = 0; a < 7; ++a) { ux[a] = prm[(f * 2 + 0) * 14 + a]; wx[a] = prm[(f * 2 + 0) * 14 + 7 + a]; }
-        const int dx = iprm[2 * f];
-#pragma unroll
-        for (int y2 = 0; y2 < 4; ++y2) {
-          float v[16];
-          tmem_ld16(tlane + (uint32_t)(f * 64 + y2 * 16), v);
-          xblend_dispatch(dx, v, ux, wx, hx[2 * y2]);
-          xblend_dispatch(dx, v + 8, ux, wx, hx[2 * y2 + 1]);
-        }
+        xblend_dispatch(iprm[2 * f], v, ux, wx, hx);
       }
-      float out[kP];
-      {
-        float uy[7], wy[7];
+      float uy[7], wy[7];
 #pragma unroll
-        for (int b = 0; b < 7; ++b) { uy[b] = prm[(f * 2 + 1) * 14 + b]; wy[b] = prm[(f * 2 + 1) * 14 + 7 + b]; }
-        yblend_dispatch(iprm[2 * f + 1], hx, uy, wy, out);
-      }
-      if (live) {   // the partner's half: xbuf[f][i][k]
-#pragma unroll
-        for (int i = 0; i < kP; ++i)
-          if (i < KEEP0 || i >= KEEP1) xbuf[(f * kP + i) * 64 + k] = out[i];
-      }
-#pragma unroll
-      for (int i = 0; i < NKEEP; ++i) keep[f][i] = out[KEEP0 + i];
+      for (int b = 0; b < 7; ++b) { uy[b] = prm[(f * 2 + 1) * 14 + b]; wy[b] = prm[(f * 2 + 1) * 14 + 7 + b]; }
+      yblend_dispatch(iprm[2 * f + 1], hx, uy, wy, out);
     } else {
 #pragma unroll
-      for (int i = 0; i < NKEEP; ++i) keep[f][i] = 0.f;
+      for (int i = 0; i < kP; ++i) out[i] = 0.f;
     }
-  }
-  tc_fence_before_sync();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(d_empty_bar);            // accumulator fully read
-  if (r128 == 0) bulk_wait_read0();                   // previous tile's row images have left shared memory
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // exchange complete, images reusable
-  if (live) {
+    if (f == 1) {               // every TMEM read of this tile has completed (tcgen05.wait::ld inside tmem_ld16)
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty_bar);
+    }
+    float* xb = xbuf + f * (kP * 64);
+    if (part == f) {
+      // hand this frame's values to the partner (same k, other part): xbuf[f][i][k]
+      if (live) {
 #pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      if (f < nf) {
+        for (int i = 0; i < kP; ++i) xb[i * 64 + k] = out[i];
+      }
+      asm volatile("bar.arrive %0, 128;" ::"r"(bar0 + f) : "memory");
+    } else {
+      asm volatile("bar.sync %0, 128;" ::"r"(bar0 + f) : "memory");
+      if (live && f < nf) {
+        uint16_t* row = img + f * (ROW_BYTES / 2);
 #pragma unroll
-        for (int i = 0; i < NKEEP; ++i) {
-          const float v = keep[f][i] + xbuf[(f * kP + KEEP0 + i) * 64 + k];
-          const int e = (KEEP0 + i) * kP + k;
+        for (int i = 0; i < kP; ++i) {
+          const float val = out[i] + xb[i * 64 + k];
           if (V16) {
-            img[f * kVolPad + e] = __half_as_ushort(__float2half_rn(v));
+            row[i * kP + k] = __half_as_ushort(__float2half_rn(val));
           } else {
-            const bf16pair sp = split_bf16(v);
-            img[f * 2 * kVolPad + e] = __bfloat16_as_ushort(sp.hi);
-            img[f * 2 * kVolPad + kVolPad + e] = __bfloat16_as_ushort(sp.lo);
+            const bf16pair sp = split_bf16(val);
+            row[i * kP + k] = __bfloat16_as_ushort(sp.hi);
+            row[kVolPad + i * kP + k] = __bfloat16_as_ushort(sp.lo);
           }
         }
       }
     }
   }
   fence_proxy_async_smem();                   // image writes -> visible to the bulk-copy (async proxy) reads
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id + 1) : "memory");
+  asm volatile("bar.sync %0, 128;" ::"r"(bar0 + 2) : "memory");
   if (r128 == 0) {
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2)
@@ -436,8 +441,7 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
         const float* prm = prm_base + (it % NPARAM) * PRM_WORDS;
         const int nf = (2 * tp + 1 < g.T) ? 2 : 1;
         uint16_t* vrow = g.vol + (((int64_t)n * g.T + 2 * tp) * kL + l) * (ROW_BYTES / 2);
-        if (q < 2) epilogue_tile<0, V16>(tmem_base, acc, q, lane, grp, nf, prm, xbuf, img, &d_empty[acc], vrow);
-        else       epilogue_tile<1, V16>(tmem_base, acc, q, lane, grp, nf, prm, xbuf, img, &d_empty[acc], vrow);
+        epilogue_tile<V16>(tmem_base, acc, q, lane, grp, nf, prm, xbuf, img, &d_empty[acc], vrow);
       }
     }
   }

@@ -56,8 +56,17 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 __device__ __forceinline__ int stg_idx(int row, int word) { return row * CW + ((word + (row >> 1)) & (CW - 1)); }
 
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int N, int row0, int col0, int lane,
-                                               float (&v)[CW], uint32_t* stg) {
+                                               float (&v)[CW], uint32_t* stg, float ln_mean = 0.f, float ln_rstd = 1.f) {
   const int row = row0 + lane;
+  if (e.ln_part) {   // LayerNorm of the A rows applied after the contraction (see GemmEpilogue)
+    const float4* w4 = reinterpret_cast<const float4*>(e.ln_wsum + col0);
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 ws = __ldg(w4 + i);
+      v[4 * i + 0] = ln_rstd * (v[4 * i + 0] - ln_mean * ws.x); v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * ws.y);
+      v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * ws.z); v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * ws.w);
+    }
+  }
   if (e.bias) {
     const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
@@ -103,6 +112,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (row0 + 8 * k + rsub < M) *reinterpret_cast<float4*>(base + k * rstep) = x[k];
+    if (e.raw_split) {
+      // the final rows once more as a split-bf16 operand + the partial LayerNorm statistics of this 16-column chunk
+      const int chunk = col0 >> 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t r = row0 + 8 * k + rsub;
+        float s1 = x[k].x + x[k].y + x[k].z + x[k].w;
+        float s2 = x[k].x * x[k].x + x[k].y * x[k].y + x[k].z * x[k].z + x[k].w * x[k].w;
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        if (r < M) {
+          uint32_t h0, l0, h1, l1;
+          split2(x[k].x, x[k].y, h0, l0);
+          split2(x[k].z, x[k].w, h1, l1);
+          __nv_bfloat16* o = e.raw_split + r * (2 * kLnDim) + col0 + 4 * q;
+          *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(o + kLnDim) = make_uint2(l0, l1);
+          if (q == 0) *reinterpret_cast<float2*>(e.stat_part + (r * kLnParts + chunk) * 2) = make_float2(s1, s2);
+        }
+      }
+    }
     __syncwarp();
   }
   if (e.out_split) {
@@ -244,12 +274,14 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       tc_fence_after_sync();
       const int row0 = mt * BM + quarter * 32;
       uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (epi.ln_part && row0 + lane < M) ln_row_stats(epi.ln_part + (int64_t)(row0 + lane) * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
 #pragma unroll 1
       for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
         float v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * CW);
         tmem_ld16(taddr, v);
-        epilogue_chunk(epi, M, N, row0, nt * BN + chunk * CW, lane, v, stg);
+        epilogue_chunk(epi, M, N, row0, nt * BN + chunk * CW, lane, v, stg, ln_mean, ln_rstd);
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty_bar[acc]);
@@ -387,12 +419,14 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       tc_fence_after_sync();
       const int row0 = mt * BM + quarter * 32;
       uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (epi.ln_part && row0 + lane < M) ln_row_stats(epi.ln_part + (int64_t)(row0 + lane) * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
 #pragma unroll 1
       for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
         float v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNP + chunk * CW);
         tmem_ld16(taddr, v);
-        epilogue_chunk(epi, M, N, row0, nt * BNP + chunk * CW, lane, v, stg);
+        epilogue_chunk(epi, M, N, row0, nt * BNP + chunk * CW, lane, v, stg, ln_mean, ln_rstd);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -541,6 +575,11 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      {
+        const int64_t grow_ln = (int64_t)mt * R + r;
+        if (epi.ln_part && grow_ln < M) ln_row_stats(epi.ln_part + grow_ln * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
+      }
       float x[kDh];
       // part 0 = q (group 0) or k (group 1); part 1 = v (group 1 only)
 #pragma unroll
@@ -552,6 +591,15 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           float v[16];
           tmem_ld16(tlane + (uint32_t)(col0 + 16 * c), v);
           const float4* b4 = reinterpret_cast<const float4*>(epi.bias + h * BNQ + col0 + 16 * c);
+          if (epi.ln_part) {
+            const float4* w4 = reinterpret_cast<const float4*>(epi.ln_wsum + h * BNQ + col0 + 16 * c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 ws = __ldg(w4 + i);
+              v[4 * i + 0] = ln_rstd * (v[4 * i + 0] - ln_mean * ws.x); v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * ws.y);
+              v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * ws.z); v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * ws.w);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b = __ldg(b4 + i);
@@ -644,6 +692,11 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
 // ------------------------------------------------------------------------------------------------
 // SIMT verification kernel: 64x64 tile, 256 threads, each 4x4 outputs; fp32 FMA on hi+lo.
 __device__ __forceinline__ void epilogue_store1(const GemmEpilogue& e, int N, int row, int col, float v) {
+  if (e.ln_part) {
+    float mean, rstd;
+    ln_row_stats(e.ln_part + (int64_t)row * kLnParts * 2, e.ln_eps, mean, rstd);
+    v = rstd * (v - mean * e.ln_wsum[col]);
+  }
   if (e.bias) v += e.bias[col];
   if (e.row_bias) v += e.row_bias[(int64_t)(row % e.row_mod) * N + col];
   v = apply_act(v, e.act);
@@ -798,7 +851,8 @@ bool qkv_time_attn_supported(int T) { return T >= 1 && T <= BM; }
 
 int gemm_qkv_time_attn_launch(const __nv_bfloat16* x_split, const __nv_bfloat16* w_heads, const float* bias_heads,
                               int M, int Kpad, int T, __nv_bfloat16* att_split, int64_t ld_split, int lo_off,
-                              float scale, int num_sms, cudaStream_t stream, const char** err) {
+                              float scale, const float* ln_part, const float* ln_wsum, float ln_eps, int num_sms,
+                              cudaStream_t stream, const char** err) {
   *err = nullptr;
   if (M <= 0 || Kpad <= 0 || (Kpad % BK) != 0 || !qkv_time_attn_supported(T) || (M % T) != 0) {
     *err = "qkv_time_attn: need M > 0, M % T == 0, 1 <= T <= 128, Kpad % 64 == 0";
@@ -830,6 +884,9 @@ int gemm_qkv_time_attn_launch(const __nv_bfloat16* x_split, const __nv_bfloat16*
   epi.out_split = att_split;
   epi.ld_split = ld_split;
   epi.lo_off = lo_off;
+  epi.ln_part = ln_part;
+  epi.ln_wsum = ln_wsum;
+  epi.ln_eps = ln_eps;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(qa::NTHREADS);
@@ -865,6 +922,14 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
   }
   if ((reinterpret_cast<uintptr_t>(p.x_split) | reinterpret_cast<uintptr_t>(p.w_split)) & 15) {
     *err = "gemm: operands must be 16-byte aligned";
+    return (int)cudaErrorInvalidValue;
+  }
+  if (p.epi.raw_split && (p.N != kLnDim || !p.epi.out_f32 || !p.epi.stat_part || impl == 1)) {
+    *err = "gemm: raw_split/stat_part need the fp32 output path of the tensor-core kernels with N == 384";
+    return (int)cudaErrorInvalidValue;
+  }
+  if (p.epi.ln_part && !p.epi.ln_wsum) {
+    *err = "gemm: ln_part needs ln_wsum";
     return (int)cudaErrorInvalidValue;
   }
   if (impl == 1) {

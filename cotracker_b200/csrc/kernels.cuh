@@ -29,6 +29,27 @@ cudaError_t launch_l2norm_rows(const float* in, int64_t rows, float* out, cudaSt
 cudaError_t launch_upsample_concat(const float* const src[4], const int c[4], const int h[4], const int w[4], int T,
                                    int H, int W, float* out, cudaStream_t s);
 
+// ---- enc_front.cu : the CNN encoder's convolutions, channels-last, on the tensor cores --------------------
+// conv1 7x7/2 pad 3 (3 -> 64), fp32 SIMT: frames [T,3,H,W] -> out [T,Ho,Wo,64] NHWC (+ bias)
+cudaError_t launch_conv_stem(const float* frames, const float* w, const float* bias, int T, int H, int W, float* out,
+                             cudaStream_t s);
+// 3x3 stride-1 pad-1 implicit-GEMM convolution: x_split [T*H*W, 2*C] (hi C | lo C), w_split [Cout, 2*9*C] packed by
+// launch_pack_conv (tap-major K), out fp32 NHWC [T,H,W,Cout] (+ bias).  C, Cout multiples of 64.
+cudaError_t launch_conv3x3_tc(const __nv_bfloat16* x_split, const __nv_bfloat16* w_split, const float* bias, int T,
+                              int H, int W, int C, int Cout, float* out, int num_sms, cudaStream_t s);
+// [Cout, Cin, taps] fp32 -> split [Cout_pad, 2*taps*Cp] with K = tap*Cp + c, zero padded
+cudaError_t launch_pack_conv(const float* w, int Cout, int Cin, int taps, int Cp, int Cout_pad, __nv_bfloat16* out,
+                             cudaStream_t s);
+// stride-2 gather (taps 9: 3x3 pad 1; taps 1: 1x1) of a split NHWC activation into GEMM rows [T*Ho*Wo, 2*taps*C]
+cudaError_t launch_gather_s2(const __nv_bfloat16* x_split, int T, int H, int W, int C, int taps, __nv_bfloat16* out,
+                             cudaStream_t s);
+// InstanceNorm + ReLU (+ residual: mode 1 x fp32; mode 2 x = 1x1/2 conv output normalised with stats_d) on NHWC rows
+cudaError_t launch_norm_act(const float* y, const float* stats, const float* x, const float* stats_d, int mode,
+                            int64_t rows, int HW, int C, float* out_f32, __nv_bfloat16* out_split, cudaStream_t s);
+// bilinear (align_corners) resize of 4 NHWC fp32 sources (c channels used, cs channel stride) + concat -> split [rows, 2*Cp]
+cudaError_t launch_upsample_concat_split(const float* const src[4], const int c[4], const int cs[4], const int h[4],
+                                         const int w[4], int T, int Cp, int H, int W, __nv_bfloat16* out, cudaStream_t s);
+
 // ---- corr.cu : correlation sampling ---------------------------------------------------------------
 // vol_split [N*T*4, 2*kVolPad] bf16, row (n*T+t)*4+level
 // impl: 0 tensor cores (correlate-then-interpolate when pyr_split is given and every level is >= 8x8: corr_tc3.cu for

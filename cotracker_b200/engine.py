@@ -57,6 +57,12 @@ def _declare(lib):
         "ct3_enc_tail_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
         "ct3_enc_tail_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
         "ct3_enc_tail": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "ct3_encoder_num_weight_tensors": (c_int, []),
+        "ct3_encoder_weight_name": (c_char_p, [c_int]),
+        "ct3_encoder_packed_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
+        "ct3_encoder_pack": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_size_t, c_void_p]),
+        "ct3_encoder_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+        "ct3_encoder": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
         "ct3_profile_enable": (c_int, [c_int]),
         "ct3_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), intp, ctypes.POINTER(ctypes.c_double)]),
     }
@@ -72,6 +78,8 @@ EXPORTED_SYMBOLS = [
     "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
     "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
     "ct3_corr_sample", "ct3_linear", "ct3_linear_prec", "ct3_split_rows", "ct3_split_rows_fp16", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
+    "ct3_encoder_num_weight_tensors", "ct3_encoder_weight_name", "ct3_encoder_packed_bytes", "ct3_encoder_pack",
+    "ct3_encoder_workspace_bytes", "ct3_encoder",
     "ct3_upsample_concat", "ct3_enc_tail_packed_bytes", "ct3_enc_tail_pack", "ct3_enc_tail_workspace_bytes", "ct3_enc_tail",
 ]
 
@@ -317,7 +325,7 @@ def updateformer(packed, x: torch.Tensor, workspace: Optional[torch.Tensor] = No
     return delta
 
 
-PROFILE_CATEGORIES = ["corr_sample", "gemm", "attention", "layernorm", "misc"]
+PROFILE_CATEGORIES = ["corr_sample", "gemm", "attention", "layernorm", "misc", "encoder"]
 
 
 def profile_enable(on: bool):
@@ -326,8 +334,8 @@ def profile_enable(on: bool):
 
 def profile_read():
     """-> ({category: ms}, {category: launches}, gemm_flops) accumulated since profile_enable(True)."""
-    ms = (ctypes.c_double * 5)()
-    n = (ctypes.c_int * 5)()
+    ms = (ctypes.c_double * len(PROFILE_CATEGORIES))()
+    n = (ctypes.c_int * len(PROFILE_CATEGORIES))()
     fl = ctypes.c_double(0)
     _check(lib().ct3_profile_read(ms, n, ctypes.byref(fl)), "ct3_profile_read")
     return dict(zip(PROFILE_CATEGORIES, list(ms))), dict(zip(PROFILE_CATEGORIES, list(n))), fl.value
@@ -363,6 +371,46 @@ def enc_tail(packed, cat: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor
     with torch.cuda.device(cat.device):
         _check(lib().ct3_enc_tail(_ptr(packed), _ptr(cat), T, H4, W4, _ptr(pyr), _ptr(workspace), workspace.numel(),
                                   _stream(cat.device)), "ct3_enc_tail")
+    return pyr
+
+
+# ---- whole encoder (enc_front.cu + GEMM engine) -----------------------------------------------------------
+def encoder_weight_names() -> List[str]:
+    L = lib()
+    return [L.ct3_encoder_weight_name(i).decode() for i in range(L.ct3_encoder_num_weight_tensors())]
+
+
+def encoder_pack(state: dict, device) -> torch.Tensor:
+    """state: mapping `fnet` state-dict key (without the `fnet.` prefix) -> tensor; returns the packed device buffer."""
+    names = encoder_weight_names()
+    ts = [state[k].detach().to(device=device, dtype=torch.float32).contiguous() for k in names]
+    n = ctypes.c_size_t(0)
+    _check(lib().ct3_encoder_packed_bytes(ctypes.byref(n)), "ct3_encoder_packed_bytes")
+    packed = torch.empty(n.value, dtype=torch.uint8, device=device)
+    ptrs = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    with torch.cuda.device(device):
+        _check(lib().ct3_encoder_pack(ptrs, len(ts), _ptr(packed), n.value, _stream(device)), "ct3_encoder_pack")
+        torch.cuda.current_stream(device).synchronize()   # `ts` may be temporaries
+    return packed
+
+
+def encoder_workspace_bytes(T: int, H: int, W: int) -> int:
+    n = ctypes.c_size_t(0)
+    _check(lib().ct3_encoder_workspace_bytes(T, H, W, ctypes.byref(n)), "ct3_encoder_workspace_bytes")
+    return n.value
+
+
+def encoder(packed: torch.Tensor, frames: torch.Tensor, workspace: torch.Tensor) -> torch.Tensor:
+    """frames [T,3,H,W] fp32 in [-1,1] -> flat channels-last L2-normalised 4-level pyramid (stride 4)."""
+    _req(frames, torch.float32, "frames")
+    T, C, H, W = frames.shape
+    if C != 3:
+        raise EngineError("frames must be [T,3,H,W]")
+    *_, total = pyramid_layout(T, H // 4, W // 4)
+    pyr = torch.empty(total, dtype=torch.float32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _check(lib().ct3_encoder(_ptr(packed), _ptr(frames), T, H, W, _ptr(pyr), _ptr(workspace), workspace.numel(),
+                                 _stream(frames.device)), "ct3_encoder")
     return pyr
 
 

@@ -6,9 +6,9 @@ Drop-in mirror of the reference's inner model API:
 with the same constructor kwargs, attributes (`model_resolution`, `window_len`, `stride`) and the same
 state-dict keys, so `load_state_dict(strict=True)` of the released checkpoints works.
 
-The nn.Module tree below is a *parameter container*: only the CNN encoder (`fnet`, a "next" row) executes
-through PyTorch.  L2-normalisation + pyramid, support sampling, correlation sampling, the correlation MLP,
-the whole EfficientUpdateFormer and the delta heads run as hand-written sm_100a CUDA behind the C ABI
+The nn.Module tree below is a *parameter container*: nothing executes through PyTorch modules.  The CNN
+encoder, L2-normalisation + pyramid, support sampling, correlation sampling, the correlation MLP, the whole
+EfficientUpdateFormer and the delta heads run as hand-written sm_100a CUDA behind the C ABI
 (`cotracker_b200.engine`).  Inference only; B must be 1 (as in the reference).
 """
 from __future__ import annotations
@@ -148,34 +148,22 @@ class CoTrackerThreeBase(nn.Module):
     def _encode(self, video: torch.Tensor, chunk: int) -> torch.Tensor:
         """video [T,3,H,W] already scaled to [-1,1] -> L2-normalised channels-last 4-level pyramid (flat fp32).
 
-        Front of the encoder (stem + residual stages + resize/concat, 40 % of its FLOPs): PyTorch/cuDNN fp32 (TF32
-        off).  Tail (conv2 3x3 416->256, InstanceNorm, ReLU, conv3 1x1, L2-normalise, 3x avg-pool): libct3_b200
-        (im2col + cta_group::2 split-bf16x3 GEMMs, csrc/enc_tail.cu).  `chunk` bounds the frames per cuDNN call
-        (reference fmaps_chunk_size)."""
-        prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
-        try:
-            H4, W4 = video.shape[-2] // self.stride, video.shape[-1] // self.stride
-            outs = []
-            for t in range(0, video.shape[0], chunk):
-                feats = [f.float().contiguous() for f in self.fnet.stages(video[t:t + chunk])]
-                outs.append(engine.upsample_concat(feats, H4, W4))   # fused resize + concat (csrc/enc_tail.cu)
-        finally:
-            torch.backends.cudnn.allow_tf32 = prev
-        cat = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
-        dev = cat.device
-        f = self.fnet
-        tail = (f.conv2.weight, f.conv2.bias, f.conv3.weight, f.conv3.bias)
-        key = (str(dev), tuple((v.data_ptr(), v._version) for v in tail))
+        The whole BasicEncoder (reference blocks.py:141-219) runs in libct3_b200.so (csrc/enc_front.cu + the GEMM
+        engine): conv1 as fp32 SIMT, every other convolution as split-bf16x3 tcgen05 GEMMs, channels-last.  The
+        library walks the clip in chunks of 16 frames itself (`chunk` = the reference's fmaps_chunk_size only bounds
+        memory there and has no numerical effect: the encoder is strictly per frame)."""
+        dev = video.device
+        sd = {k: v for k, v in self.fnet.state_dict().items()}
+        key = (str(dev), tuple((v.data_ptr(), v._version) for v in self.fnet.parameters()))
         if self._enc_packed is None or self._enc_key != key:
-            self._enc_packed = engine.enc_tail_pack(*tail, dev)
+            self._enc_packed = engine.encoder_pack(sd, dev)
             self._enc_key = key
-        T, _, H4, W4 = cat.shape
-        need = engine.enc_tail_workspace_bytes(T, H4, W4)
+        T, _, H, W = video.shape
+        need = engine.encoder_workspace_bytes(T, H, W)
         if self._enc_ws is None or self._enc_ws.numel() < need or self._enc_ws.device != dev:
             self._enc_ws = None
             self._enc_ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        return engine.enc_tail(self._enc_packed, cat, self._enc_ws)
+        return engine.encoder(self._enc_packed, video.contiguous(), self._enc_ws)
 
     def _check_inputs(self, video, queries, is_train):
         if is_train:

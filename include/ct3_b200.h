@@ -154,7 +154,7 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
  * kernel category: 0 corr_sample, 1 gemm (tcgen05), 2 attention, 3 layernorm, 4 misc.
  * ct3_profile_enable(1) clears and starts recording; ct3_profile_read synchronises and sums. */
 int ct3_profile_enable(int on);
-int ct3_profile_read(double ms[5], int launches[5], double* gemm_flops);
+int ct3_profile_read(double ms[6], int launches[6], double* gemm_flops);
 
 /* ---- stage-level entry points (used by the parity tests and profiles) ------- */
 
@@ -189,6 +189,21 @@ int ct3_split_rows_fp16(const float* x, int rows, int K, int Kpad, void* x_split
  * delta out [N, T, 4] fp32. */
 int ct3_updateformer(const void* packed, const float* x, int T, int N, float* delta, void* workspace,
                      size_t workspace_bytes, ct3_stream_t stream);
+
+/* ---- the whole CNN encoder (BasicEncoder.forward, blocks.py:190-219; normalise + pyramid,
+ * cotracker3_offline.py:92-117) on the tensor-core engine, channels-last ------------------------------------
+ * frames [T,3,H,W] fp32 already scaled to [-1,1] (cotracker3_offline.py:63) -> pyr (ct3_pyramid_layout(T, H/4, W/4)).
+ * conv1 7x7/2 runs as fp32 SIMT, every other convolution as split-bf16x3 tcgen05 GEMMs (3x3 stride-1: implicit GEMM
+ * over TMA-shifted NHWC boxes; strided ones: gather + GEMM); InstanceNorm statistics in fp64.
+ * Weight tensors in the order of ct3_encoder_weight_name() (state-dict keys below `fnet.`). */
+int ct3_encoder_num_weight_tensors(void);
+const char* ct3_encoder_weight_name(int index);
+int ct3_encoder_packed_bytes(size_t* out_bytes);
+int ct3_encoder_pack(const float* const* tensors_host_array_of_device_ptrs, int n_tensors, void* packed,
+                     size_t packed_bytes, ct3_stream_t stream);
+int ct3_encoder_workspace_bytes(int T, int H, int W, size_t* out_bytes);
+int ct3_encoder(const void* packed, const float* frames, int T, int H, int W, float* pyr, void* workspace,
+                size_t workspace_bytes, ct3_stream_t stream);
 
 #ifdef __cplusplus
 }

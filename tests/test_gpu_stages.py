@@ -344,9 +344,12 @@ def test_update_loop_cluster_gemm_vs_simt_at_scale(eng):
     assert e_c < 5e-4 and e_v < 5e-4
 
 
-def test_encoder_tail_matches_torch(eng):
-    """conv2 -> InstanceNorm -> ReLU -> conv3 -> L2-normalise -> pyramid through the GEMM engine vs fp32 PyTorch on the
-    same GPU (same front features); covers the cta_group::2 path (M = T*H4*W4 rows) and odd map sizes."""
+def test_encoder_matches_torch(eng):
+    """The whole BasicEncoder + L2-normalise + pyramid in libct3_b200 (conv1 SIMT, implicit-GEMM 3x3 convolutions on
+    TMA-shifted NHWC boxes, gather + GEMM for the strided ones, InstanceNorm/ReLU/residual kernels, fused
+    resize + concat) vs the fp32 PyTorch module holding the same weights (cuDNN, TF32 off) on the same GPU.  Odd map
+    sizes exercise partial tiles, zero padding through TMA out-of-bounds fill and the strided-conv size arithmetic;
+    18 frames = two 16-frame chunks."""
     from cotracker_b200.build import build_cotracker
     from cotracker_b200.synthetic import seeded_state_dict, texture_video
     m = build_cotracker(None, offline=True, window_len=60)
