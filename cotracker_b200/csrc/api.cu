@@ -31,9 +31,11 @@ constexpr OptDef kOptDefs[OPT_COUNT] = {
     // switch: SURVEY 7.3 measured that every transformer GEMM breaks the 1e-3 px budget with fewer than 3 products.
     {"prec.corr", 1, 3},   // the 49x128x49 correlation contraction (corr_tc2.cu)
     {"prec.fc1", 1, 3},    // corr_mlp.fc1 (K = 2401): 1|2 also make the correlation volume a single fp16 plane
-    {"fuse", 0, 1},        // 1: q|k|v projection + time attention in one kernel (gemm_qkv_time_attn_kernel); 0: separate
+    // 0: separate LayerNorm / projection / attention kernels; 1: q|k|v projection + time attention in one kernel
+    // (gemm_qkv_time_attn_kernel); 2: additionally every LayerNorm folded into the GEMMs around it (no LN kernels)
+    {"fuse", 0, 2},
 };
-thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1, 1};
+thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1, 2};
 #define g_opt_gemm g_opt[OPT_GEMM]
 #define g_opt_corr g_opt[OPT_CORR]
 #define g_opt_attn g_opt[OPT_ATTN]
@@ -90,12 +92,14 @@ size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // packed-weights layout
 struct Lin {
   size_t w = 0, b = 0;  // byte offsets: split weights [N, 2*Kpad] bf16 ; bias [N] fp32
+  size_t ws = 0;        // fp32 [N]: sum_k W[n][k], the correction vector of a LayerNorm folded into this layer
   int N = 0, K = 0, Kpad = 0;
 };
 struct Block {
   Lin qkv_h;  // time blocks only: q|k|v regrouped per head, rows h*144 + [q_h(48) | k_h(48) | v_h(48)] (fused attention)
   Lin q;    // self-attention blocks: fused q|k|v (N = 1152); cross blocks: to_q (N = 384)
   Lin kv;   // cross blocks only: to_kv (N = 768)
+  Lin kv_f; // cross blocks only: to_kv with the affine norm_context folded in (W diag(gamma), b + W beta)
   Lin out, fc1, fc2;
   size_t ctx_g = 0, ctx_b = 0;  // cross blocks: norm_context weight / bias (fp32 [384])
   bool cross = false;
@@ -105,6 +109,7 @@ struct Layout {
   Lin corr_fc1_h;   // corr_mlp.fc1 once more as split fp16 planes (prec.fc1 = 1 | 2); shares corr_fc1's bias
   Block time[kDepth], vself[kDepth], p2v[kDepth], v2p[kDepth];
   size_t heads_w = 0, heads_b = 0, virt = 0, win_f32 = 0;
+  size_t scratch = 0;   // pack-time scratch: one folded to_kv weight [768, 384] + bias [768] in fp32
   size_t total = 0;
 };
 
@@ -118,6 +123,8 @@ void place_lin(Lin& l, int N, int K, size_t& off) {
   off = align_up(off + (size_t)N * 2 * l.Kpad * sizeof(__nv_bfloat16));
   l.b = off;
   off = align_up(off + (size_t)N * sizeof(float));
+  l.ws = off;
+  off = align_up(off + (size_t)N * sizeof(float));
 }
 void place_block(Block& b, bool cross, size_t& off, bool time = false) {
   b.cross = cross;
@@ -127,6 +134,7 @@ void place_block(Block& b, bool cross, size_t& off, bool time = false) {
     b.ctx_b = off; off = align_up(off + kC * sizeof(float));
     place_lin(b.q, kC, kC, off);
     place_lin(b.kv, 2 * kC, kC, off);
+    place_lin(b.kv_f, 2 * kC, kC, off);
   } else {
     place_lin(b.q, 3 * kC, kC, off);
   }
@@ -152,6 +160,8 @@ const Layout& layout() {
       place_block(L.p2v[i], true, off);
       place_block(L.v2p[i], true, off);
     }
+    L.scratch = off;
+    off = align_up(off + (size_t)2 * kC * kC * sizeof(float) + (size_t)2 * kC * sizeof(float));
     L.total = off;
     return L;
   }();
@@ -194,6 +204,8 @@ struct Workspace {
   __nv_bfloat16* h1;      // [N*T*4, 2*384]
   __nv_bfloat16* xs;      // [N*T, 2*1152]
   float* tokens;          // [(N+64)*T, 384]
+  __nv_bfloat16* traw;    // [(N+64)*T, 2*384]  the token rows once more as a split operand (LayerNorm fold)
+  float* tstat;           // [(N+64)*T, 24, 2]  partial (sum, sum of squares) of every token row
   __nv_bfloat16* ln;      // [(N+64)*T, 2*384]
   __nv_bfloat16* att;     // [(N+64)*T, 2*384]
   float* qkv;             // [(N+64)*T, 1152]   (also point q [N*T,384] / point kv [N*T,768])
@@ -214,6 +226,8 @@ Workspace carve(void* base, int T, int N, int H4 = 0, int W4 = 0) {
   w.h1 = (__nv_bfloat16*)take(Mc * 2 * kCorrHid * 2);
   w.xs = (__nv_bfloat16*)take(Rp * 2 * kXPad * 2);
   w.tokens = (float*)take(R * kC * 4);
+  w.traw = (__nv_bfloat16*)take(R * 2 * kC * 2);
+  w.tstat = (float*)take(R * kLnParts * 2 * 4);
   w.ln = (__nv_bfloat16*)take(R * 2 * kC * 2);
   w.att = (__nv_bfloat16*)take(R * 2 * kC * 2);
   w.qkv = (float*)take(R * 3 * kC * 4);
@@ -309,12 +323,12 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
     {  // ---- time block over every token row (points + virtual): sequence = track (cotracker.py:494-495)
       const Block& b = L.time[i];
       RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
-      if (g_opt[OPT_FUSE] == 1 && R.impl == 0 && g_opt_attn == 0 && qkv_time_attn_supported(T)) {
+      if (g_opt[OPT_FUSE] >= 1 && R.impl == 0 && g_opt_attn == 0 && qkv_time_attn_supported(T)) {
         // q|k|v projection and the per-track T x T attention in ONE kernel: fp32 q|k|v never reaches HBM
         ProfScope ps(R.s, CAT_GEMM, 2.0 * (double)Rall * 3 * kC * kC);
         int rc = gemm_qkv_time_attn_launch(W.ln, reinterpret_cast<const __nv_bfloat16*>(pk + b.qkv_h.w),
                                            reinterpret_cast<const float*>(pk + b.qkv_h.b), Rall, kC, T, W.att, 2 * kC,
-                                           kC, scale, num_sms(), R.s, &R.gerr);
+                                           kC, scale, nullptr, nullptr, 0.f, num_sms(), R.s, &R.gerr);
         if (rc != 0) {
           snprintf(g_err, sizeof(g_err), "fused qkv + time attention failed: %s (%s)",
                    cudaGetErrorString((cudaError_t)rc), R.gerr ? R.gerr : "");
@@ -400,6 +414,101 @@ Prec effective_prec(bool have_pyr_split, int T, int H4, int W4) {
   return p;
 }
 
+// LayerNorm-folded variant of transformer_body (option fuse = 2, tensor-core kernels, T <= 128): no LayerNorm kernel
+// runs.  Every GEMM that writes token rows (input_transform, to_out, mlp.fc2) also emits them as a split-bf16 operand
+// plus partial row statistics (GemmEpilogue::raw_split / stat_part); every GEMM that consumes LN(x) multiplies the
+// RAW rows and applies  rstd * (W.x - mean * wsum) + b  in its epilogue; the affine norm_context of the cross blocks
+// (cotracker.py:539-540) is folded into to_kv's weights and bias at pack time (Block::kv_f).
+bool fold_enabled(const Runner& R, int T) {
+  return g_opt[OPT_FUSE] == 2 && R.impl == 0 && g_opt_attn == 0 && qkv_time_attn_supported(T);
+}
+
+int transformer_body_fold(Runner& R, const Workspace& W, int T, int N) {
+  const Layout& L = R.L;
+  const int Rp = N * T, Rv = kV * T, Rall = Rp + Rv;
+  const float scale = 1.0f / sqrtf((float)kDh);
+  const uint8_t* pk = R.pk;
+  RUNC(CAT_MISC, launch_init_virtual(W.tokens, reinterpret_cast<const float*>(pk + L.virt), T, N, R.s));
+  float* vtok = W.tokens + (int64_t)Rp * kC;
+  __nv_bfloat16* raw_p = W.traw;
+  __nv_bfloat16* raw_v = W.traw + (int64_t)Rp * 2 * kC;
+  float* st_p = W.tstat;
+  float* st_v = W.tstat + (int64_t)Rp * kLnParts * 2;
+  __nv_bfloat16* att_p = W.att;
+  __nv_bfloat16* att_v = W.att + (int64_t)Rp * 2 * kC;
+  RUNC(CAT_LN, launch_rowstats_split(vtok, Rv, raw_v, st_v, R.s));
+  auto ln = [&](GemmEpilogue e, const float* part, const Lin& lin, float eps) {
+    e.ln_part = part; e.ln_wsum = reinterpret_cast<const float*>(pk + lin.ws); e.ln_eps = eps;
+    return e;
+  };
+  auto prod = [&](GemmEpilogue e, __nv_bfloat16* raw, float* stat) { e.raw_split = raw; e.stat_part = stat; return e; };
+  // x += mlp(LN(x)) on rows [row0, row0 + rows)
+  auto mlp = [&](const Block& b, int64_t row0, int rows) -> int {
+    float* x = W.tokens + row0 * kC;
+    __nv_bfloat16* raw = W.traw + row0 * 2 * kC;
+    float* st = W.tstat + row0 * kLnParts * 2;
+    __nv_bfloat16* hm = W.hmid + row0 * 2 * kMlpHid;
+    RUNC(-1, R.gemm(raw, b.fc1, rows, ln(Runner::to_split(hm, 2 * kMlpHid, kMlpHid, /*tanh*/ 2), st, b.fc1, 1e-6f)));
+    RUNC(-1, R.gemm(hm, b.fc2, rows, prod(Runner::to_f32(x, kC, true), raw, st)));
+    return 0;
+  };
+  auto attention = [&](const float* q, int q_ld, const float* kv, int kv_ld, int k_col, int v_col, __nv_bfloat16* out,
+                       int Lq, int Lk) -> int {
+    AttnParams a{};
+    a.q = q; a.q_ld = q_ld; a.q_col = 0;
+    a.kv = kv; a.kv_ld = kv_ld; a.k_col = k_col; a.v_col = v_col;
+    a.out = out; a.out_ld = 2 * kC; a.lo_off = kC;
+    a.num_seq = T; a.Lq = Lq; a.Lk = Lk;
+    a.q_seq_stride = 1; a.q_tok_stride = T; a.k_seq_stride = 1; a.k_tok_stride = T;
+    a.scale = scale;
+    RUNC(CAT_ATTN, run_attention(R, W, a, false));
+    return 0;
+  };
+  for (int i = 0; i < kDepth; ++i) {
+    {  // ---- time block (cotracker.py:494-495)
+      const Block& b = L.time[i];
+      {
+        ProfScope ps(R.s, CAT_GEMM, 2.0 * (double)Rall * 3 * kC * kC);
+        int rc = gemm_qkv_time_attn_launch(W.traw, reinterpret_cast<const __nv_bfloat16*>(pk + b.qkv_h.w),
+                                           reinterpret_cast<const float*>(pk + b.qkv_h.b), Rall, kC, T, W.att, 2 * kC,
+                                           kC, scale, W.tstat, reinterpret_cast<const float*>(pk + b.qkv_h.ws), 1e-6f,
+                                           num_sms(), R.s, &R.gerr);
+        if (rc != 0) {
+          snprintf(g_err, sizeof(g_err), "fused qkv + time attention failed: %s (%s)",
+                   cudaGetErrorString((cudaError_t)rc), R.gerr ? R.gerr : "");
+          return CT3_ECUDA;
+        }
+      }
+      RUNC(-1, R.gemm(W.att, b.out, Rall, prod(Runner::to_f32(W.tokens, kC, true), W.traw, W.tstat)));
+      if (int rc = mlp(b, 0, Rall)) return rc;
+    }
+    {  // ---- virtual <- point cross attention (cotracker.py:510-512)
+      const Block& b = L.v2p[i];
+      RUNC(-1, R.gemm(raw_v, b.q, Rv, ln(Runner::to_f32(W.vqkv, kC, false), st_v, b.q, 1e-6f)));
+      RUNC(-1, R.gemm(raw_p, b.kv_f, Rp, ln(Runner::to_f32(W.qkv, 2 * kC, false), st_p, b.kv_f, 1e-5f)));
+      if (int rc = attention(W.vqkv, kC, W.qkv, 2 * kC, 0, kC, att_v, kV, N)) return rc;
+      RUNC(-1, R.gemm(att_v, b.out, Rv, prod(Runner::to_f32(vtok, kC, true), raw_v, st_v)));
+      if (int rc = mlp(b, Rp, Rv)) return rc;
+    }
+    {  // ---- virtual self attention (cotracker.py:514)
+      const Block& b = L.vself[i];
+      RUNC(-1, R.gemm(raw_v, b.q, Rv, ln(Runner::to_f32(W.vqkv, 3 * kC, false), st_v, b.q, 1e-6f)));
+      if (int rc = attention(W.vqkv, 3 * kC, W.vqkv, 3 * kC, kC, 2 * kC, att_v, kV, kV)) return rc;
+      RUNC(-1, R.gemm(att_v, b.out, Rv, prod(Runner::to_f32(vtok, kC, true), raw_v, st_v)));
+      if (int rc = mlp(b, Rp, Rv)) return rc;
+    }
+    {  // ---- point <- virtual cross attention (cotracker.py:515-517)
+      const Block& b = L.p2v[i];
+      RUNC(-1, R.gemm(raw_p, b.q, Rp, ln(Runner::to_f32(W.qkv, kC, false), st_p, b.q, 1e-6f)));
+      RUNC(-1, R.gemm(raw_v, b.kv_f, Rv, ln(Runner::to_f32(W.vqkv, 2 * kC, false), st_v, b.kv_f, 1e-5f)));
+      if (int rc = attention(W.qkv, kC, W.vqkv, 2 * kC, 0, kC, att_p, N, kV)) return rc;
+      RUNC(-1, R.gemm(att_p, b.out, Rp, prod(Runner::to_f32(W.tokens, kC, true), raw_p, st_p)));
+      if (int rc = mlp(b, 0, Rp)) return rc;
+    }
+  }
+  return 0;
+}
+
 int check_TN(int T, int N) {
   if (T < 1 || N < 1) return fail(CT3_EINVAL, "T and N must be >= 1%s");
   if ((int64_t)(N + kV) * T * 3 * kC >= (int64_t)1 << 40) return fail(CT3_EINVAL, "problem too large%s");
@@ -467,6 +576,8 @@ int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t 
                      int fp16 = 0) -> cudaError_t {
     cudaError_t e = launch_split_rows(w, rows, l.K, l.Kpad, perm, reinterpret_cast<__nv_bfloat16*>(pk + l.w), row_off, s, fp16);
     if (e != cudaSuccess) return e;
+    e = launch_rowsum(w, rows, l.K, reinterpret_cast<float*>(pk + l.ws) + row_off, s);
+    if (e != cudaSuccess) return e;
     return cudaMemcpyAsync(pk + l.b + (size_t)row_off * 4, b, (size_t)rows * 4, cudaMemcpyDeviceToDevice, s);
   };
   auto put_f32 = [&](size_t off, const float* src, size_t count) {
@@ -507,6 +618,12 @@ int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t 
     if ((e = put_f32(b.ctx_b, t[k + 1], kC)) != cudaSuccess) return e;
     if ((e = put_lin(b.q, t[k + 2], t[k + 3], kC, 0, 0)) != cudaSuccess) return e;
     if ((e = put_lin(b.kv, t[k + 4], t[k + 5], 2 * kC, 0, 0)) != cudaSuccess) return e;
+    {   // to_kv(norm_context(x)) with the affine part folded into the layer (stream-ordered reuse of the scratch)
+      float* w2 = reinterpret_cast<float*>(pk + L.scratch);
+      float* b2 = w2 + (size_t)2 * kC * kC;
+      if ((e = launch_affine_fold(t[k + 4], t[k + 5], t[k], t[k + 1], 2 * kC, kC, w2, b2, s)) != cudaSuccess) return e;
+      if ((e = put_lin(b.kv_f, w2, b2, 2 * kC, 0, 0)) != cudaSuccess) return e;
+    }
     if ((e = put_lin(b.out, t[k + 6], t[k + 7], kC, 0, 0)) != cudaSuccess) return e;
     if ((e = put_lin(b.fc1, t[k + 8], t[k + 9], kMlpHid, 0, 0)) != cudaSuccess) return e;
     if ((e = put_lin(b.fc2, t[k + 10], t[k + 11], kC, 0, 0)) != cudaSuccess) return e;
@@ -694,9 +811,10 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
       GemmEpilogue e = Runner::to_f32(W.tokens, kC, false);
       e.row_bias = W.row_bias;
       e.row_mod = T;
+      if (fold_enabled(R, T)) { e.raw_split = W.traw; e.stat_part = W.tstat; }
       RUNC(-1, R.gemm(W.xs, L.in_tr, Rp, e));
     }
-    if (int rc = transformer_body(R, W, T, N)) return rc;
+    if (int rc = fold_enabled(R, T) ? transformer_body_fold(R, W, T, N) : transformer_body(R, W, T, N)) return rc;
     // (v) heads + state update
     RUNC(CAT_MISC, launch_heads(W.tokens, reinterpret_cast<const float*>(pk + L.heads_w),
                      reinterpret_cast<const float*>(pk + L.heads_b), coords, vis, conf, nullptr, T, N, R.s));
@@ -715,8 +833,12 @@ int ct3_updateformer(const void* packed, const float* x, int T, int N, float* de
   Runner R{reinterpret_cast<const uint8_t*>(packed), L, (cudaStream_t)stream, g_opt_gemm};
   const int Rp = N * T;
   RUNC(CAT_MISC, launch_split_rows(x, Rp, kX, kXPad, /*perm_x*/ 1, W.xs, 0, R.s));
-  RUNC(-1, R.gemm(W.xs, L.in_tr, Rp, Runner::to_f32(W.tokens, kC, false)));
-  if (int rc = transformer_body(R, W, T, N)) return rc;
+  {
+    GemmEpilogue e = Runner::to_f32(W.tokens, kC, false);
+    if (fold_enabled(R, T)) { e.raw_split = W.traw; e.stat_part = W.tstat; }
+    RUNC(-1, R.gemm(W.xs, L.in_tr, Rp, e));
+  }
+  if (int rc = fold_enabled(R, T) ? transformer_body_fold(R, W, T, N) : transformer_body(R, W, T, N)) return rc;
   RUNC(CAT_MISC, launch_heads(W.tokens, reinterpret_cast<const float*>(R.pk + L.heads_w),
                    reinterpret_cast<const float*>(R.pk + L.heads_b), nullptr, nullptr, nullptr, delta, T, N, R.s));
   return 0;

@@ -129,8 +129,8 @@ cudaError_t launch_corr_sample(const float* pyr, const __nv_bfloat16* pyr_split,
                                const uint8_t* track_valid, const float* coords, int T, int N,
                                __nv_bfloat16* vol_split, int impl, int mode, int vol16, int num_sms, cudaStream_t s) {
   if (corr_uses_patch_kernel(impl, pyr_split != nullptr, T, H4, W4)) {
-    if (impl == 0 && mode == 2)
-      return launch_corr_patch_t(pyr_split, H4, W4, support, track_valid, coords, T, N, vol_split, vol16, num_sms, s);
+    if (impl == 0 && mode != 3)
+      return launch_corr_patch_t(pyr_split, H4, W4, support, track_valid, coords, T, N, vol_split, vol16, mode == 1, num_sms, s);
     return launch_corr_patch_tc(pyr_split, H4, W4, support, track_valid, coords, T, N, vol_split, mode, vol16, num_sms, s);
   }
   if (vol16) return cudaErrorInvalidValue;   // only the patch kernel writes the single-plane volume

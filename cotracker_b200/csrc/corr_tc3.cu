@@ -13,53 +13,54 @@
 //
 //   pyramid  : ONE fp16 plane per level [T][H][W][128] (made once per update-loop call); texels are rounded to fp16
 //              (2^-12 relative), the support vectors are exact to a split fp16 pair (prec.corr = 2)
-//   B tile   [128 texel rows x 128 ch] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, K-half) is
-//              ONE 4-D TMA box (64 ch x 8 x 8 x 1) landing in the 128B-swizzled K-major operand layout; ring of 6
-//              K-half slots (16 KiB), each freed as soon as its 4 MMAs retire
-//   A tile   [128 x 128 ch] : rows 0..63 hi plane / 64..127 lo plane of the 49 support vectors of (n,l) (rows 49..63
-//              of each half zero), built once per unit by 2 warps
-//   D        [128 x 128] fp32 in TMEM: lanes 0..63 = S_hi . F, lanes 64..127 = S_lo . F, columns = texels; ONE
-//              tcgen05.mma (M=128, N=128) per k16 step, 4 accumulators
-//   epilogue : 2 groups x 4 warps alternate tiles; thread = (part hi|lo, k).  Per frame: 4 x tcgen05.ld (two texel
-//              rows each) -> x-blend -> y-blend -> 49 sampled correlations of this part.  A border clamp only turns
-//              the tap indices into a clamped SHIFT of the interior pattern (idx = clamp(a + d, 0, 7), d uniform per
-//              frame and axis), so every case -- interior, any border, far outside -- runs the same register code
-//              through a warp-uniform switch on d; the per-sample weights (exactly tap_pair() of corr_tc2.cu,
-//              canonicalised to the shift pattern; tests/test_host_logic.py brute-forces that this always works)
-//              are computed once per tile by the otherwise idle lanes of the TMA warp.
-//              The hi and lo parts of a support vector sit in different warps: for frame 0 the hi part hands its 49
-//              values to the lo part through shared memory, for frame 1 the other way round, and the receiver adds,
-//              converts and writes the row image -- all four warps do the same work.  The blend code exists once
-//              (58 KB of SASS: frame loop not unrolled).  Volume rows leave as bulk shared->global copies.
-// Warps: 0 TMA issuer (+ tap tables), 1 MMA issuer (+TMEM alloc), 2..3 support builders, 4..11 epilogue.
+//   B tile   [128 texel rows x 64 ch] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, K-half) is ONE
+//              4-D TMA box (64 ch x 8 x 8 x 1) landing in the 128B-swizzled K-major operand layout; ring of 6 K-half
+//              slots (16 KiB), each freed as soon as its MMAs retire
+//   A tiles  4 x [128 x 64 ch] : {hi, lo} plane x K-half of the 49 support vectors of (n,l) in rows 0..48 (rows 49..127
+//              stay zero), built once per unit by 2 warps.  The hi and lo planes are CONCATENATED ALONG K:
+//              D += S_hi[kh] . F[kh]^T  and  D += S_lo[kh] . F[kh]^T  accumulate into the same TMEM lanes, so lane k
+//              holds the complete (S_hi + S_lo)[k] . F and the epilogue needs no exchange between warps.
+//              (prec.corr = 1 skips the lo MMAs: single fp16 product.)
+//   D        [128 x 128] fp32 in TMEM, lanes 0..48 live, columns = texels (f*64 + y*8 + x); 4 accumulators
+//   epilogue : 3 groups x 2 warps (TMEM lane quarters 0 and 1) take tiles round-robin; thread = support vector k.
+//              Per frame: 4 x tcgen05.ld (two texel rows each) -> x-blend -> y-blend -> 49 sampled correlations ->
+//              convert -> volume-row image in shared memory -> bulk shared->global copy of the whole 9.5 KiB row.
+//              A border clamp only turns the tap indices into a clamped SHIFT of the interior pattern
+//              (idx = clamp(a + d, 0, 7), d uniform per frame and axis), so every case -- interior, any border, far
+//              outside -- runs the same register code through a warp-uniform switch on d; the per-sample weights
+//              (exactly grid_sample's border-clamped taps, canonicalised to the shift pattern;
+//              tests/test_host_logic.py brute-forces that this always works) are computed once per tile by the
+//              otherwise idle lanes of the TMA warp.  The blend code exists ONCE (frame loop not unrolled): a fully
+//              unrolled epilogue is 290 KB of SASS and ran 5x slower on instruction-cache misses
+//              (profiles/r2_corr_tc3_history.txt).
+// Warps (10): 0,1 / 4,5 / 8,9 epilogue groups (warp % 4 = TMEM lane quarter), 2 TMA issuer (+ tap tables), 3 MMA issuer
+// (+ TMEM alloc), 6,7 support builders.
 #include "gemm.cuh"
 #include "kernels.cuh"
 
 namespace ct3 {
 namespace {
 
-constexpr int TMA_WARP = 0;
-constexpr int MMA_WARP = 1;
-constexpr int SB_WARP0 = 2;
-constexpr int EPI_WARP0 = 4;              // warps 4..7 group 0, 8..11 group 1; (warp & 3) = TMEM lane quarter
-constexpr int THREADS = 12 * 32;
+constexpr int TMA_WARP = 2;
+constexpr int MMA_WARP = 3;
+constexpr int SB_WARP0 = 6;               // warps 6, 7 build the support operand
+constexpr int NGROUP = 3;                 // epilogue groups: warps {0,1}, {4,5}, {8,9}
+constexpr int THREADS = 10 * 32;
 constexpr int NSLOT = 6;                  // texel ring: slots of one K-half (64 channels) of a 2-frame tile
 constexpr int A_SLOT = 16384;             // [128 texel rows x 128 B] fp16
-constexpr int S_HALF = 16384;             // one K-half of S: [hi rows 0..63 | lo rows 64..127] x 128 B
-constexpr int S_BYTES = 2 * S_HALF;
+constexpr int S_TILE = 16384;             // one (plane, K-half) of S: [128 rows x 128 B], rows 49..127 zero
+constexpr int S_BYTES = 4 * S_TILE;       // tile index = plane * 2 + K-half
 constexpr int NACC = 4;
 constexpr uint32_t TMEM_COLS = NACC * 128;
 constexpr int NPARAM = 8;                 // tap-table ring (a tile's slot is rewritten only after its epilogue read it)
 constexpr int PRM_WORDS = 64;             // per tile: [frame 2][axis 2]{u[7], w[7]} = 56 floats, d[2][2] ints, flag
-constexpr int X_GROUP = 2 * kP * 64 * 4;  // exchange buffer per group: [frame 2][i 49][k 64] fp32 = 25088 B
 constexpr int ROW_BYTES_SPLIT = 2 * kVolPad * 2;   // 9728
 constexpr int ROW_BYTES_H16 = kVolPad * 2;         // 4864
 constexpr int IMG_GROUP = 2 * ROW_BYTES_SPLIT;
 constexpr int OFF_A = 0;
 constexpr int OFF_S = OFF_A + NSLOT * A_SLOT;
-constexpr int OFF_X = OFF_S + S_BYTES;
-constexpr int OFF_IMG = OFF_X + 2 * X_GROUP;
-constexpr int OFF_PARAM = OFF_IMG + 2 * IMG_GROUP;
+constexpr int OFF_IMG = OFF_S + S_BYTES;
+constexpr int OFF_PARAM = OFF_IMG + NGROUP * IMG_GROUP;
 constexpr int OFF_BAR = OFF_PARAM + NPARAM * PRM_WORDS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -162,86 +163,61 @@ __device__ __forceinline__ void yblend_dispatch(int d, const float (&hx)[8][7], 
   }
 }
 
-// Epilogue of one 2-frame tile for one thread = (part hi|lo of support vector k).  The blend code exists ONCE (the
-// frame loop is not unrolled; a fully unrolled version is 290 KB of SASS and thrashes the instruction cache: measured
-// 10.7 ms per launch instead of ~1).  Per frame both parts blend their 49 values; then the part that equals the frame
-// index stores them to `xbuf` and the OTHER part adds its own, converts and writes the volume-row image -- so the lo
-// warps finalise frame 0 and the hi warps frame 1, and all four warps do the same work.
+// Epilogue of one 2-frame tile for one thread = support vector k (TMEM lane k).  The blend code exists ONCE (the
+// frame loop is not unrolled; see the file header).
 template <bool V16>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int acc, int q, int lane, int grp, int nf,
-                                              const float* prm, float* xbuf, uint16_t* img, uint64_t* d_empty_bar,
-                                              uint16_t* vrow) {
+                                              const float* prm, uint16_t* img, uint64_t* d_empty_bar, uint16_t* vrow) {
   constexpr int ROW_BYTES = V16 ? ROW_BYTES_H16 : ROW_BYTES_SPLIT;
-  const int part = q >> 1;                            // 0: S_hi rows (TMEM lanes 0..63), 1: S_lo rows
-  const int k = (q & 1) * 32 + lane;
+  const int k = q * 32 + lane;                        // q in {0, 1}
   const bool live = k < kP;
-  const int r128 = q * 32 + lane;
-  const int bar0 = 1 + 3 * grp;                       // named barriers of this group: frame 0, frame 1, tile end
+  const int bar_id = 1 + grp;                         // named barrier of this group (64 threads)
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
   const int* iprm = reinterpret_cast<const int*>(prm) + 56;
   if (iprm[4] == 0) asm volatile("trap;");   // a sample outside the shift pattern: impossible (see file header)
-  if (r128 == 0) bulk_wait_read0();          // previous tile's row images have left shared memory
+  if (k == 0) bulk_wait_read0();             // previous tile's row images have left shared memory ...
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");   // ... before anyone overwrites them
 #pragma unroll 1
-  for (int f = 0; f < 2; ++f) {
-    float out[kP];
-    if (f < nf) {
-      float hx[8][7];
-      {
-        float v[64];
+  for (int f = 0; f < nf; ++f) {
+    float hx[8][7];
+    {
+      float v[64];
+      tmem_ld64(tlane + (uint32_t)(f * 64), v);
+      float ux[7], wx[7];
 #pragma unroll
-        for (int y2 = 0; y2 < 4; ++y2) {
-          float t16[16];
-          tmem_ld16(tlane + (uint32_t)(f * 64 + y2 * 16), t16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[y2 * 16 + j] = t16[j];
-        }
-        float ux[7], wx[7];
-#pragma unroll
-        for (int a = 0; a < 7; ++a) { ux[a] = prm[(f * 2 + 0) * 14 + a]; wx[a] = prm[(f * 2 + 0) * 14 + 7 + a]; }
-        xblend_dispatch(iprm[2 * f], v, ux, wx, hx);
-      }
-      float uy[7], wy[7];
-#pragma unroll
-      for (int b = 0; b < 7; ++b) { uy[b] = prm[(f * 2 + 1) * 14 + b]; wy[b] = prm[(f * 2 + 1) * 14 + 7 + b]; }
-      yblend_dispatch(iprm[2 * f + 1], hx, uy, wy, out);
-    } else {
-#pragma unroll
-      for (int i = 0; i < kP; ++i) out[i] = 0.f;
+      for (int a = 0; a < 7; ++a) { ux[a] = prm[(f * 2 + 0) * 14 + a]; wx[a] = prm[(f * 2 + 0) * 14 + 7 + a]; }
+      xblend_dispatch(iprm[2 * f], v, ux, wx, hx);
     }
-    if (f == 1) {               // every TMEM read of this tile has completed (tcgen05.wait::ld inside tmem_ld16)
+    float uy[7], wy[7];
+#pragma unroll
+    for (int b = 0; b < 7; ++b) { uy[b] = prm[(f * 2 + 1) * 14 + b]; wy[b] = prm[(f * 2 + 1) * 14 + 7 + b]; }
+    const int dy = iprm[2 * f + 1];
+    if (f == nf - 1) {
+      // every TMEM read of this tile has completed (tcgen05.wait::ld inside tmem_ld64) and nothing below reads the
+      // tap table any more: releasing the accumulator is also what eventually lets the TMA warp recycle the table slot
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty_bar);
     }
-    float* xb = xbuf + f * (kP * 64);
-    if (part == f) {
-      // hand this frame's values to the partner (same k, other part): xbuf[f][i][k]
-      if (live) {
+    float out[kP];
+    yblend_dispatch(dy, hx, uy, wy, out);
+    if (live) {
+      uint16_t* row = img + f * (ROW_BYTES / 2);
 #pragma unroll
-        for (int i = 0; i < kP; ++i) xb[i * 64 + k] = out[i];
-      }
-      asm volatile("bar.arrive %0, 128;" ::"r"(bar0 + f) : "memory");
-    } else {
-      asm volatile("bar.sync %0, 128;" ::"r"(bar0 + f) : "memory");
-      if (live && f < nf) {
-        uint16_t* row = img + f * (ROW_BYTES / 2);
-#pragma unroll
-        for (int i = 0; i < kP; ++i) {
-          const float val = out[i] + xb[i * 64 + k];
-          if (V16) {
-            row[i * kP + k] = __half_as_ushort(__float2half_rn(val));
-          } else {
-            const bf16pair sp = split_bf16(val);
-            row[i * kP + k] = __bfloat16_as_ushort(sp.hi);
-            row[kVolPad + i * kP + k] = __bfloat16_as_ushort(sp.lo);
-          }
+      for (int i = 0; i < kP; ++i) {
+        if (V16) {
+          row[i * kP + k] = __half_as_ushort(__float2half_rn(out[i]));
+        } else {
+          const bf16pair sp = split_bf16(out[i]);
+          row[i * kP + k] = __bfloat16_as_ushort(sp.hi);
+          row[kVolPad + i * kP + k] = __bfloat16_as_ushort(sp.lo);
         }
       }
     }
   }
   fence_proxy_async_smem();                   // image writes -> visible to the bulk-copy (async proxy) reads
-  asm volatile("bar.sync %0, 128;" ::"r"(bar0 + 2) : "memory");
-  if (r128 == 0) {
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  if (k == 0) {
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2)
       if (t2 < nf) bulk_store_s2g(vrow + (int64_t)t2 * kL * (ROW_BYTES / 2), reinterpret_cast<uint8_t*>(img) + t2 * ROW_BYTES, ROW_BYTES);
@@ -249,7 +225,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int acc, int q
   }
 }
 
-template <bool V16>
+template <bool V16, bool ONEPROD>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__ Corr3Maps maps, int num_units) {
   constexpr int ROW_BYTES = V16 ? ROW_BYTES_H16 : ROW_BYTES_SPLIT;
@@ -259,7 +235,7 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
   uint64_t* a_full = bars;                          // [NSLOT] TMA -> MMA         (count 1 + tx bytes)
   uint64_t* a_empty = bars + NSLOT;                 // [NSLOT] MMA -> TMA         (tcgen05.commit)
   uint64_t* d_full = bars + 2 * NSLOT;              // [NACC] MMA -> epilogue group  (tcgen05.commit)
-  uint64_t* d_empty = bars + 2 * NSLOT + NACC;      // [NACC] epilogue group -> MMA  (count 4)
+  uint64_t* d_empty = bars + 2 * NSLOT + NACC;      // [NACC] epilogue group -> MMA  (count 2)
   uint64_t* s_full = bars + 2 * NSLOT + 2 * NACC;       // builders -> MMA, per unit  (count 2)
   uint64_t* s_empty = bars + 2 * NSLOT + 2 * NACC + 1;  // MMA -> builders, per unit  (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * NACC + 2);
@@ -267,9 +243,9 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_unit = (g.T + 1) / 2;
 
-  // one-time: zero S (rows 49..63 of each half stay zero forever) and the two row images (K padding stays zero)
+  // one-time: zero S (rows 49..127 of every tile stay zero forever) and the row images (K padding stays zero)
   for (int i = threadIdx.x; i < S_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_S)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 2 * IMG_GROUP / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_IMG)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < NGROUP * IMG_GROUP / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_IMG)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) {
@@ -278,7 +254,7 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
     }
     for (int i = 0; i < NACC; ++i) {
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], 4);
+      mbar_init(&d_empty[i], 2);
     }
     mbar_init(s_full, 2);
     mbar_init(s_empty, 1);
@@ -313,9 +289,9 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
           box_origin8(cy0, H, by0, dy0);
           box_origin8(cx1, W, bx1, dx1);
           box_origin8(cy1, H, by1, dy1);
-          // the first K-half slot of this tile doubles as the "previous epilogue has read the table slot" gate:
-          // slot it % NPARAM was last used by tile it - 8, whose accumulator (and therefore its table) was consumed
-          // before accumulator it - 4 could be reissued (NACC = 4 < NPARAM)
+          // The first K-half slot of this tile doubles as the gate of the table slot: slot it % 8 was last used by
+          // tile it - 8; the ring slot waited for here was freed by the MMAs of tile it - 3, which were issued after
+          // tile it - 4's, which needed the accumulator that tile it - 8's epilogue had released after reading its table.
           mbar_wait_spin(&a_empty[hc % NSLOT], ((hc / NSLOT) & 1u) ^ 1u);
           {
             float* prm = reinterpret_cast<float*>(smem + OFF_PARAM) + (it % NPARAM) * PRM_WORDS;
@@ -354,7 +330,6 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
           hc += 2;        // every lane tracks the slot counter (the table gate above is a warp-wide wait)
           __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp == MMA_WARP) {
@@ -377,10 +352,12 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
             const uint32_t f_base = smem_u32(smem + OFF_A + sl * A_SLOT);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              // D[support row][texel] += [S_hi ; S_lo](128 x 16) * F(128 texels x 16)^T
-              const uint64_t ds = umma_desc_sw128(s_base + (uint32_t)(kh * S_HALF + j * 32));
+              // D[support k][texel] += S_lo[k] . F^T + S_hi[k] . F^T over this K-half (hi and lo concatenated along K)
               const uint64_t df = umma_desc_sw128(f_base + j * 32);
-              umma_bf16(d_tmem, ds, df, idesc, (kh | j) != 0 ? 1u : 0u);
+              if (!ONEPROD)
+                umma_bf16(d_tmem, umma_desc_sw128(s_base + (uint32_t)((2 + kh) * S_TILE + j * 32)), df, idesc, (kh | j) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, umma_desc_sw128(s_base + (uint32_t)(kh * S_TILE + j * 32)), df, idesc,
+                        (!ONEPROD || (kh | j) != 0) ? 1u : 0u);
             }
             umma_commit(&a_empty[sl]);
           }
@@ -389,11 +366,11 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
         umma_commit(s_empty);
       }
     }
-  } else if (warp < EPI_WARP0) {
+  } else if (warp == SB_WARP0 || warp == SB_WARP0 + 1) {
     // ================================================================== support builders (A operand, once per unit)
     const int sb = warp - SB_WARP0;
     const int atom = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;  // where this lane's 4 channels live
-    uint8_t* s_hi = smem + OFF_S;
+    uint8_t* s0 = smem + OFF_S;
     uint32_t ui = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
       const int n = u / kL, l = u % kL;
@@ -414,9 +391,9 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
           uint32_t h0, l0, h1, l1;
           split2_h(rows[j].x, rows[j].y, h0, l0);
           split2_h(rows[j].z, rows[j].w, h1, l1);
-          const uint32_t off = (uint32_t)(atom * S_HALF) + sw128(p, chunk) + (uint32_t)(half * 8);
-          *reinterpret_cast<uint2*>(s_hi + off) = make_uint2(h0, h1);          // rows 0..63 of the K-half: hi plane
-          *reinterpret_cast<uint2*>(s_hi + 8192 + off) = make_uint2(l0, l1);   // rows 64..127: lo plane
+          const uint32_t off = (uint32_t)(atom * S_TILE) + sw128(p, chunk) + (uint32_t)(half * 8);   // K-half = atom
+          *reinterpret_cast<uint2*>(s0 + off) = make_uint2(h0, h1);                 // hi plane tiles 0, 1
+          *reinterpret_cast<uint2*>(s0 + 2 * S_TILE + off) = make_uint2(l0, l1);    // lo plane tiles 2, 3
         }
       }
       fence_proxy_async_smem();
@@ -424,43 +401,42 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
       if (lane == 0) mbar_arrive(s_full);
     }
   } else {
-    // ================================================================== epilogue
-    const int grp = (warp - EPI_WARP0) >> 2;   // tiles with (it & 1) == grp
-    const int q = warp & 3;                    // TMEM lane quarter; quarters 0,1 = S_hi rows, 2,3 = S_lo rows
-    float* xbuf = reinterpret_cast<float*>(smem + OFF_X + grp * X_GROUP);
+    // ================================================================== epilogue: warps {0,1}, {4,5}, {8,9}
+    const int grp = warp >> 2;                 // tiles with it % NGROUP == grp
+    const int q = warp & 3;                    // TMEM lane quarter 0 or 1
     uint16_t* img = reinterpret_cast<uint16_t*>(smem + OFF_IMG + grp * IMG_GROUP);
     const float* prm_base = reinterpret_cast<const float*>(smem + OFF_PARAM);
     uint32_t it = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int n = u / kL, l = u % kL;
       for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
-        if ((int)(it & 1u) != grp) continue;
+        if ((int)(it % NGROUP) != grp) continue;
         const int acc = it % NACC;
         mbar_wait(&d_full[acc], (it / NACC) & 1u);
         tc_fence_after_sync();
         const float* prm = prm_base + (it % NPARAM) * PRM_WORDS;
         const int nf = (2 * tp + 1 < g.T) ? 2 : 1;
         uint16_t* vrow = g.vol + (((int64_t)n * g.T + 2 * tp) * kL + l) * (ROW_BYTES / 2);
-        epilogue_tile<V16>(tmem_base, acc, q, lane, grp, nf, prm, xbuf, img, &d_empty[acc], vrow);
+        epilogue_tile<V16>(tmem_base, acc, q, lane, grp, nf, prm, img, &d_empty[acc], vrow);
       }
     }
+    if (q == 0 && lane == 0) bulk_wait0();     // outstanding volume-row copies of this group
   }
 
-  if (warp >= EPI_WARP0 && (threadIdx.x & 127) == 0) bulk_wait0();   // outstanding volume-row copies
   tc_fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <bool V16>
+template <bool V16, bool ONEPROD>
 cudaError_t launch_variant(const Corr3Args& g, const Corr3Maps& maps, int num_units, int num_sms, cudaStream_t s) {
   static DeviceOnce attr;
   cudaError_t e = once_per_device(attr, [&] {
-    return cudaFuncSetAttribute(corr_patch_t_kernel<V16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    return cudaFuncSetAttribute(corr_patch_t_kernel<V16, ONEPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (e != cudaSuccess) return e;
   const int grid = num_units < num_sms ? num_units : num_sms;
-  corr_patch_t_kernel<V16><<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
+  corr_patch_t_kernel<V16, ONEPROD><<<grid, THREADS, SMEM_BYTES, s>>>(g, maps, num_units);
   return cudaGetLastError();
 }
 
@@ -468,7 +444,7 @@ cudaError_t launch_variant(const Corr3Args& g, const Corr3Maps& maps, int num_un
 
 cudaError_t launch_corr_patch_t(const __nv_bfloat16* pyr_half, int H4, int W4, const float* support,
                                 const uint8_t* track_valid, const float* coords, int T, int N,
-                                __nv_bfloat16* vol, int vol16, int num_sms, cudaStream_t s) {
+                                __nv_bfloat16* vol, int vol16, int one_product, int num_sms, cudaStream_t s) {
   Corr3Args g;
   g.lay = pyramid_layout(T, H4, W4);
   g.support = support;
@@ -489,8 +465,11 @@ cudaError_t launch_corr_patch_t(const __nv_bfloat16* pyr_half, int H4, int W4, c
       return cudaErrorInvalidValue;
   }
   const int num_units = N * kL;
-  return vol16 ? launch_variant<true>(g, maps, num_units, num_sms, s)
-               : launch_variant<false>(g, maps, num_units, num_sms, s);
+  if (one_product)
+    return vol16 ? launch_variant<true, true>(g, maps, num_units, num_sms, s)
+                 : launch_variant<false, true>(g, maps, num_units, num_sms, s);
+  return vol16 ? launch_variant<true, false>(g, maps, num_units, num_sms, s)
+               : launch_variant<false, false>(g, maps, num_units, num_sms, s);
 }
 
 }  // namespace ct3

@@ -78,14 +78,19 @@ cudaError_t launch_corr_patch_tc(const __nv_bfloat16* pyr_split, int H4, int W4,
                                  __nv_bfloat16* vol_split, int mode, int vol16, int num_sms, cudaStream_t s);
 
 // corr_tc3.cu: the production kernel -- same algorithm with the MMA transposed (supports = M side), one fp16 texel
-// plane (pyr_split made with mode 2), split-fp16 supports: the numerics of mode 2
+// plane (pyr_split made with mode 1 or 2), supports split fp16 (mode 2) or one fp16 plane (one_product, mode 1)
 cudaError_t launch_corr_patch_t(const __nv_bfloat16* pyr_half, int H4, int W4, const float* support,
                                 const uint8_t* track_valid, const float* coords, int T, int N,
-                                __nv_bfloat16* vol, int vol16, int num_sms, cudaStream_t s);
+                                __nv_bfloat16* vol, int vol16, int one_product, int num_sms, cudaStream_t s);
 
 // ---- tokens.cu : elementwise / row-wise pieces of the transformer ---------------------------------
 cudaError_t launch_layernorm_split(const float* x, int rows, const float* gamma, const float* beta, float eps,
                                    __nv_bfloat16* out_split, cudaStream_t s);
+// LayerNorm fold helpers: split copy + partial row statistics of fp32 token rows; rowsum / affine fold at pack time
+cudaError_t launch_rowstats_split(const float* x, int rows, __nv_bfloat16* raw_split, float* stat_part, cudaStream_t s);
+cudaError_t launch_rowsum(const float* w, int N, int K, float* out, cudaStream_t s);
+cudaError_t launch_affine_fold(const float* w, const float* b, const float* gamma, const float* beta, int N, int K,
+                               float* w2, float* b2, cudaStream_t s);
 cudaError_t launch_build_x_small(const float* coords, const float* vis, const float* conf, int T, int N,
                                  __nv_bfloat16* x_split, cudaStream_t s);
 cudaError_t launch_init_virtual(float* tokens, const float* virt, int T, int N, cudaStream_t s);

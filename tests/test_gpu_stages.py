@@ -241,7 +241,7 @@ def test_updateformer_attention_shapes(eng, attn, N, T):
 
 
 @pytest.mark.parametrize("N,T", [(70, 6), (333, 16), (130, 40), (50, 48), (21, 100), (9, 128), (5, 129)])
-def test_fused_qkv_time_attention(eng, N, T):
+def test_fused_time_attention_and_layernorm_fold(eng, N, T):
     """gemm_qkv_time_attn_kernel (projection + per-track attention in one kernel; tile = floor(128/T) whole tracks,
     ragged last tile, T = 128 -> one track per tile; T = 129 falls back to the separate kernels) against the oracle
     and against the unfused path (`fuse` = 0)."""
@@ -252,15 +252,16 @@ def test_fused_qkv_time_attention(eng, N, T):
         want = O.updateformer(sd, x[None])[0]
     packed = eng.pack_weights(sd, DEV)
     got = {}
-    for fuse in (1, 0):
+    for fuse in (2, 1, 0):     # 2: + every LayerNorm folded into the GEMMs (default), 1: fused time attention, 0: all separate
         eng.set_option("fuse", fuse)
         try:
             got[fuse] = eng.updateformer(packed, x.to(DEV)).cpu()
         finally:
-            eng.set_option("fuse", 1)
+            eng.set_option("fuse", 2)
     scale = max(float(want.abs().max()), 1.0)
-    assert float((got[1] - want).abs().max()) < 2e-4 * scale, (N, T, float((got[1] - want).abs().max()), scale)
-    assert float((got[1] - got[0]).abs().max()) < 1e-4 * scale
+    for fuse in (2, 1):
+        assert float((got[fuse] - want).abs().max()) < 2e-4 * scale, (fuse, N, T, float((got[fuse] - want).abs().max()), scale)
+        assert float((got[fuse] - got[0]).abs().max()) < 1e-4 * scale, fuse
 
 
 def test_corr_mlp_gelu_variant_is_erf(eng):
