@@ -232,6 +232,8 @@ def main():
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--online", action="store_true", help="BASELINE config C4: cotracker3_online, window 16 / step 8")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option for A/B runs, e.g. --opt fuse=1 --opt prec.fc1=2 (ct3_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -251,6 +253,9 @@ def main():
     from cotracker_b200.synthetic import seeded_state_dict, texture_video
 
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
+    for kv in args.opt:
+        name, value = kv.split("=")
+        engine.set_option(name, int(value))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -373,7 +378,7 @@ def main():
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": prec["dtype"], "data": "synthetic",
-        "config": workload_config(T, G, world, online),
+        "config": dict(workload_config(T, G, world, online), **({"options": args.opt} if args.opt else {})),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": tr.numel() * 4 + vis.numel()},
         "gpu_launches": int(sum(cat_n.values())),

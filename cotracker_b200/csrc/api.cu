@@ -25,7 +25,7 @@ constexpr OptDef kOptDefs[OPT_COUNT] = {
     {"gemm", 0, 1},   // 0 tcgen05, 1 SIMT verification
     {"corr", 0, 3},   // 0 tcgen05 correlate-then-interpolate (corr_tc3.cu / corr_tc2.cu), 1 exact-fp32 SIMT, 2 corr_tc.cu,
                       // 3 correlate-then-interpolate with corr_tc2.cu for every precision mode (A/B)
-    {"attn", 0, 1},   // 0 tensor-core kernels, 1 exact-fp32 SIMT verification
+    {"attn", 0, 2},   // 0 tensor-core kernels, 1 exact-fp32 SIMT verification, 2 = 0 + tcgen05 point<-virtual attention (A/B)
     // tensor-core products per FLOP of a GEMM group: 3 = split x split (hi*hi + lo*hi + hi*lo),
     // 2 = fp16 activation plane x split fp16 weights, 1 = single fp16 product.  Only the correlation branch has the
     // switch: SURVEY 7.3 measured that every transformer GEMM breaks the 1e-3 px budget with fewer than 3 products.
@@ -35,7 +35,7 @@ constexpr OptDef kOptDefs[OPT_COUNT] = {
     // (gemm_qkv_time_attn_kernel); 2: additionally every LayerNorm folded into the GEMMs around it (no LN kernels)
     {"fuse", 0, 2},
 };
-thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1, 2};
+thread_local int g_opt[OPT_COUNT] = {0, 0, 0, kDefPrecCorr, kDefPrecFc1, 1};   // fuse = 2 measured slower
 #define g_opt_gemm g_opt[OPT_GEMM]
 #define g_opt_corr g_opt[OPT_CORR]
 #define g_opt_attn g_opt[OPT_ATTN]
@@ -107,6 +107,7 @@ struct Block {
 struct Layout {
   Lin corr_fc1, corr_fc2, in_tr;
   Lin corr_fc1_h;   // corr_mlp.fc1 once more as split fp16 planes (prec.fc1 = 1 | 2); shares corr_fc1's bias
+  Lin corr_fc1_t, corr_fc1_th;   // the same two with the columns in corr_tc3.cu's support-major volume order
   Block time[kDepth], vself[kDepth], p2v[kDepth], v2p[kDepth];
   size_t heads_w = 0, heads_b = 0, virt = 0, win_f32 = 0;
   size_t scratch = 0;   // pack-time scratch: one folded to_kv weight [768, 384] + bias [768] in fp32
@@ -148,6 +149,8 @@ const Layout& layout() {
     size_t off = 0;
     place_lin(L.corr_fc1, kCorrHid, kVol, off);
     place_lin(L.corr_fc1_h, kCorrHid, kVol, off);
+    place_lin(L.corr_fc1_t, kCorrHid, kVol, off);
+    place_lin(L.corr_fc1_th, kCorrHid, kVol, off);
     place_lin(L.corr_fc2, kCorrOut, kCorrHid, off);
     place_lin(L.in_tr, kC, kX, off);
     L.win_f32 = off; off = align_up(off + (size_t)kC * kX * sizeof(float));
@@ -292,6 +295,8 @@ struct Runner {
 
 int run_attention(Runner& R, const Workspace& W, const AttnParams& a, bool per_warp) {
   if (g_opt_attn == 1) return (int)launch_attention(a, R.s);
+  // point <- virtual (64 keys per frame, thousands of queries): experimental tcgen05 kernel (attention_p2v.cu), opt-in
+  if (g_opt_attn == 2 && !per_warp && a.Lq > kV && attention_p2v_supported(a)) return (int)launch_attention_p2v(a, R.s);
   return (int)launch_attention_tc(a, per_warp, W.att_part, num_sms(), R.s);
 }
 
@@ -323,7 +328,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
     {  // ---- time block over every token row (points + virtual): sequence = track (cotracker.py:494-495)
       const Block& b = L.time[i];
       RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
-      if (g_opt[OPT_FUSE] >= 1 && R.impl == 0 && g_opt_attn == 0 && qkv_time_attn_supported(T)) {
+      if (g_opt[OPT_FUSE] >= 1 && R.impl == 0 && g_opt_attn != 1 && qkv_time_attn_supported(T)) {
         // q|k|v projection and the per-track T x T attention in ONE kernel: fp32 q|k|v never reaches HBM
         ProfScope ps(R.s, CAT_GEMM, 2.0 * (double)Rall * 3 * kC * kC);
         int rc = gemm_qkv_time_attn_launch(W.ln, reinterpret_cast<const __nv_bfloat16*>(pk + b.qkv_h.w),
@@ -405,7 +410,11 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
 
 // effective precision of the correlation branch for this thread's options: the single-plane / fewer-product modes
 // exist in corr_tc2.cu only, so whenever another correlation kernel runs the branch computes split x split
-struct Prec { int corr, fc1; bool patch; bool vol16() const { return fc1 < 3; } };
+struct Prec {
+  int corr, fc1; bool patch;
+  bool vol16() const { return fc1 < 3; }
+  bool support_major() const { return patch && corr != 3 && g_opt_corr == 0; }   // corr_tc3.cu writes k*49 + i
+};
 Prec effective_prec(bool have_pyr_split, int T, int H4, int W4) {
   Prec p;
   p.patch = corr_uses_patch_kernel(g_opt_corr, have_pyr_split, T, H4, W4);
@@ -420,7 +429,7 @@ Prec effective_prec(bool have_pyr_split, int T, int H4, int W4) {
 // RAW rows and applies  rstd * (W.x - mean * wsum) + b  in its epilogue; the affine norm_context of the cross blocks
 // (cotracker.py:539-540) is folded into to_kv's weights and bias at pack time (Block::kv_f).
 bool fold_enabled(const Runner& R, int T) {
-  return g_opt[OPT_FUSE] == 2 && R.impl == 0 && g_opt_attn == 0 && qkv_time_attn_supported(T);
+  return g_opt[OPT_FUSE] == 2 && R.impl == 0 && g_opt_attn != 1 && qkv_time_attn_supported(T);
 }
 
 int transformer_body_fold(Runner& R, const Workspace& W, int T, int N) {
@@ -540,6 +549,13 @@ int ct3_get_option(const char* name, int* value) {
   return fail(CT3_EINVAL, "unknown option %s", name);
 }
 
+int ct3_volume_is_support_major(int T, int H4, int W4, int* flag) {
+  if (!flag) return fail(CT3_EINVAL, "null argument%s");
+  if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
+  *flag = effective_prec(true, T, H4, W4).support_major() ? 1 : 0;
+  return 0;
+}
+
 int ct3_precision_info(int T, int H4, int W4, int* corr_products, int* fc1_products, int* volume_bytes_per_element) {
   if (int rc = ct3_pyramid_layout(T, H4, W4, nullptr, nullptr, nullptr, nullptr)) return rc;
   const Prec pr = effective_prec(true, T, H4, W4);
@@ -585,7 +601,9 @@ int ct3_pack_weights(const float* const* t, int n_tensors, void* packed, size_t 
   };
   int k = 0;
   CK(put_lin(L.corr_fc1, t[k], t[k + 1], kCorrHid, 0, 0), "pack corr_fc1");
-  CK(put_lin(L.corr_fc1_h, t[k], t[k + 1], kCorrHid, 0, 0, /*fp16*/ 1), "pack corr_fc1 (fp16 planes)"); k += 2;
+  CK(put_lin(L.corr_fc1_h, t[k], t[k + 1], kCorrHid, 0, 0, /*fp16*/ 1), "pack corr_fc1 (fp16 planes)");
+  CK(put_lin(L.corr_fc1_t, t[k], t[k + 1], kCorrHid, 0, /*volume transpose*/ 2), "pack corr_fc1 (support-major)");
+  CK(put_lin(L.corr_fc1_th, t[k], t[k + 1], kCorrHid, 0, 2, /*fp16*/ 1), "pack corr_fc1 (support-major, fp16)"); k += 2;
   CK(put_lin(L.corr_fc2, t[k], t[k + 1], kCorrOut, 0, 0), "pack corr_fc2"); k += 2;
   CK(put_lin(L.in_tr, t[k], t[k + 1], kC, 0, /*perm_x*/ 1), "pack input_transform");
   CK(put_f32(L.win_f32, t[k], (size_t)kC * kX), "pack input_transform fp32"); k += 2;
@@ -793,11 +811,11 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
                                       pr.corr, pr.vol16() ? 1 : 0, num_sms(), R.s));
     // (iii) corr_mlp: 2401 -> 384 (GELU erf) -> 256, written straight into X columns [256*l, 256*l+256)
     if (pr.vol16()) {   // single fp16 volume plane x split fp16 weights: 2 (or 1) tensor-core products per FLOP
-      GemmEpilogue e1 = Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1);
-      e1.bias = reinterpret_cast<const float*>(pk + L.corr_fc1.b);
-      RUNC(-1, R.gemm(W.vol, L.corr_fc1_h, Mc, e1, pr.fc1, /*fp16*/ 1, kVolPad));
+      RUNC(-1, R.gemm(W.vol, pr.support_major() ? L.corr_fc1_th : L.corr_fc1_h, Mc,
+                      Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1), pr.fc1, /*fp16*/ 1, kVolPad));
     } else {
-      RUNC(-1, R.gemm(W.vol, L.corr_fc1, Mc, Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
+      RUNC(-1, R.gemm(W.vol, pr.support_major() ? L.corr_fc1_t : L.corr_fc1, Mc,
+                      Runner::to_split(W.h1, 2 * kCorrHid, kCorrHid, /*erf*/ 1)));
     }
     {
       GemmEpilogue e = Runner::to_split(W.xs, 2 * kXPad, kXPad, 0);
@@ -862,7 +880,7 @@ const EncLayout& enc_layout() {
   }();
   return E0;
 }
-struct EncWs { __nv_bfloat16* a; float* y; __nv_bfloat16* ys; float* stats; size_t total; int tc; };
+struct EncWs { __nv_bfloat16* a; float* y; __nv_bfloat16* ys; float* stats; void* stat_scratch; size_t total; int tc; };
 EncWs enc_carve(void* base, int T, int H4, int W4) {
   EncWs w;
   w.tc = T < 16 ? T : 16;                         // frames per chunk: bounds the im2col operand to ~3 GB
@@ -874,6 +892,7 @@ EncWs enc_carve(void* base, int T, int H4, int W4) {
   w.y = (float*)take(Mc * kEncMid * 4);
   w.ys = (__nv_bfloat16*)take(Mc * 2 * kEncMid * 2);
   w.stats = (float*)take((size_t)w.tc * kEncMid * 2 * 4);
+  w.stat_scratch = take(instnorm_scratch_bytes(w.tc, kEncMid));
   w.total = off;
   return w;
 }
@@ -949,7 +968,7 @@ int ct3_enc_tail(const void* packed, const float* cat, int T, int H4, int W4, fl
     p.epi.out_f32 = W.y; p.epi.ld_f32 = kEncMid;
     int rc = gemm_launch(p, g_opt_gemm, num_sms(), s, &gerr);
     if (rc != 0) { snprintf(g_err, sizeof(g_err), "enc conv2 gemm: %s (%s)", cudaGetErrorString((cudaError_t)rc), gerr ? gerr : ""); return CT3_ECUDA; }
-    CK(launch_instnorm_stats(W.y, tc, HW, kEncMid, 1e-5f, W.stats, s), "instnorm stats");
+    CK(launch_instnorm_stats(W.y, tc, HW, kEncMid, 1e-5f, W.stats, W.stat_scratch, s), "instnorm stats");
     CK(launch_instnorm_relu_split(W.y, W.stats, (int64_t)Mc, HW, kEncMid, W.ys, s), "instnorm relu split");
     GemmProblem q;
     q.x_split = W.ys;
@@ -1045,6 +1064,7 @@ EncGeom enc_geom(int H, int W) {
 }
 struct EncFullWs {
   float *fy, *fyd, *fx[4], *stats, *stats_d;
+  void* stat_scratch;
   __nv_bfloat16 *sx, *sy, *gat, *gat_d, *cat;
   size_t total; int tc;
 };
@@ -1079,6 +1099,7 @@ EncFullWs enc_full_carve(void* base, int T, int H, int W) {
   w.cat = (__nv_bfloat16*)take(P4 * 2 * kCatCp * 2);
   w.stats = (float*)take((size_t)w.tc * 256 * 2 * 4);
   w.stats_d = (float*)take((size_t)w.tc * 256 * 2 * 4);
+  w.stat_scratch = take(instnorm_scratch_bytes(w.tc, 256));
   w.total = off;
   return w;
 }
@@ -1167,7 +1188,7 @@ int ct3_encoder(const void* packed, const float* frames, int T, int H, int W, fl
     return 0;
   };
   const int chunks = (T + Wk.tc - 1) / Wk.tc;
-  ProfScope ps_all(s, CAT_ENC, 0.0, chunks * 69 + 3);   // kernels launched per 16-frame chunk + the 3 pyramid pools
+  ProfScope ps_all(s, CAT_ENC, 0.0, chunks * 90 + 3);   // kernels launched per 16-frame chunk + the 3 pyramid pools
   for (int t0 = 0; t0 < T; t0 += Wk.tc) {
     const int tc = (T - t0) < Wk.tc ? (T - t0) : Wk.tc;
     // ---- stem: conv1 7x7/2 -> IN -> ReLU
@@ -1175,7 +1196,7 @@ int ct3_encoder(const void* packed, const float* frames, int T, int H, int W, fl
     int64_t rows = (int64_t)tc * h * w;
     CK(launch_conv_stem(frames + (int64_t)t0 * 3 * H * W, reinterpret_cast<const float*>(pk + E.stem_w),
                         reinterpret_cast<const float*>(pk + E.stem_b), tc, H, W, Wk.fy, s), "conv1");
-    CK(launch_instnorm_stats(Wk.fy, tc, h * w, C, 1e-5f, Wk.stats, s), "stem stats");
+    CK(launch_instnorm_stats(Wk.fy, tc, h * w, C, 1e-5f, Wk.stats, Wk.stat_scratch, s), "stem stats");
     CK(launch_norm_act(Wk.fy, Wk.stats, nullptr, nullptr, 0, rows, h * w, C, Wk.fx[0], Wk.sx, s), "stem norm");
     // ---- four stages of two residual units
     for (int st = 0; st < 4; ++st) {
@@ -1189,22 +1210,22 @@ int ct3_encoder(const void* packed, const float* frames, int T, int H, int W, fl
         CK(launch_gather_s2(Wk.sx, tc, h, w, Cin, 9, Wk.gat, s), "gather 3x3/2");
         CK(launch_gather_s2(Wk.sx, tc, h, w, Cin, 1, Wk.gat_d, s), "gather 1x1/2");
         if (int rc = gemm_rows(Wk.gat, E.unit[st][0][0], orows, Wk.fy)) return rc;
-        CK(launch_instnorm_stats(Wk.fy, tc, ho * wo, Cp, 1e-5f, Wk.stats, s), "stats");
+        CK(launch_instnorm_stats(Wk.fy, tc, ho * wo, Cp, 1e-5f, Wk.stats, Wk.stat_scratch, s), "stats");
         CK(launch_norm_act(Wk.fy, Wk.stats, nullptr, nullptr, 0, orows, ho * wo, Cp, nullptr, Wk.sy, s), "norm");
         CK(launch_conv3x3_tc(Wk.sy, W16(E.unit[st][0][1]), B32(E.unit[st][0][1]), tc, ho, wo, Cp, Cp, Wk.fy, nsm, s), "conv");
-        CK(launch_instnorm_stats(Wk.fy, tc, ho * wo, Cp, 1e-5f, Wk.stats, s), "stats");
+        CK(launch_instnorm_stats(Wk.fy, tc, ho * wo, Cp, 1e-5f, Wk.stats, Wk.stat_scratch, s), "stats");
         if (int rc = gemm_rows(Wk.gat_d, E.down[st], orows, Wk.fyd)) return rc;
-        CK(launch_instnorm_stats(Wk.fyd, tc, ho * wo, Cp, 1e-5f, Wk.stats_d, s), "stats");
+        CK(launch_instnorm_stats(Wk.fyd, tc, ho * wo, Cp, 1e-5f, Wk.stats_d, Wk.stat_scratch, s), "stats");
         CK(launch_norm_act(Wk.fy, Wk.stats, Wk.fyd, Wk.stats_d, 2, orows, ho * wo, Cp, X, Wk.sx, s), "norm");
         h = ho; w = wo; rows = orows;
       }
       for (int u = (st > 0 ? 1 : 0); u < 2; ++u) {
         // stride-1 unit: out = relu(x + relu(IN(conv(relu(IN(conv(x)))))))
         CK(launch_conv3x3_tc(Wk.sx, W16(E.unit[st][u][0]), B32(E.unit[st][u][0]), tc, h, w, Cp, Cp, Wk.fy, nsm, s), "conv");
-        CK(launch_instnorm_stats(Wk.fy, tc, h * w, Cp, 1e-5f, Wk.stats, s), "stats");
+        CK(launch_instnorm_stats(Wk.fy, tc, h * w, Cp, 1e-5f, Wk.stats, Wk.stat_scratch, s), "stats");
         CK(launch_norm_act(Wk.fy, Wk.stats, nullptr, nullptr, 0, rows, h * w, Cp, nullptr, Wk.sy, s), "norm");
         CK(launch_conv3x3_tc(Wk.sy, W16(E.unit[st][u][1]), B32(E.unit[st][u][1]), tc, h, w, Cp, Cp, Wk.fy, nsm, s), "conv");
-        CK(launch_instnorm_stats(Wk.fy, tc, h * w, Cp, 1e-5f, Wk.stats, s), "stats");
+        CK(launch_instnorm_stats(Wk.fy, tc, h * w, Cp, 1e-5f, Wk.stats, Wk.stat_scratch, s), "stats");
         CK(launch_norm_act(Wk.fy, Wk.stats, X, nullptr, 1, rows, h * w, Cp, X, Wk.sx, s), "norm");
       }
     }
@@ -1214,7 +1235,7 @@ int ct3_encoder(const void* packed, const float* frames, int T, int H, int W, fl
     const float* srcs[4] = {Wk.fx[0], Wk.fx[1], Wk.fx[2], Wk.fx[3]};
     CK(launch_upsample_concat_split(srcs, kStageC, kStageCp, g.h, g.w, tc, kCatCp, g.H4, g.W4, Wk.cat, s), "upsample concat");
     CK(launch_conv3x3_tc(Wk.cat, W16(E.conv2), B32(E.conv2), tc, g.H4, g.W4, kCatCp, kEncMid, Wk.fy, nsm, s), "conv2");
-    CK(launch_instnorm_stats(Wk.fy, tc, HW4, kEncMid, 1e-5f, Wk.stats, s), "instnorm stats");
+    CK(launch_instnorm_stats(Wk.fy, tc, HW4, kEncMid, 1e-5f, Wk.stats, Wk.stat_scratch, s), "instnorm stats");
     CK(launch_instnorm_relu_split(Wk.fy, Wk.stats, Mc, HW4, kEncMid, Wk.sy, s), "instnorm relu split");
     float* f0 = pyr + lay.off[0] + (int64_t)t0 * HW4 * kD;
     {

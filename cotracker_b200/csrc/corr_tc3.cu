@@ -1,7 +1,10 @@
 // corr_tc3.cu -- fused bilinear sampling + 4-D correlation, production kernel ("CorrBlock.sample" of the north star):
 //
-//   vol[(n,t,l)][(a*7+b)*49 + k] = < bilinear(F_l[t], cx/2^l + a-3, cy/2^l + b-3) , S_l[n, k, :] >
+//   vol[(n,t,l)][k*49 + (a*7+b)] = < bilinear(F_l[t], cx/2^l + a-3, cy/2^l + b-3) , S_l[n, k, :] >
 //   (get_correlation_feat + einsum, cotracker3_online.py:130-143, cotracker3_offline.py:144-156)
+// NB the volume row is SUPPORT-MAJOR here (the reference and the other correlation kernels emit (a*7+b)*49 + k): a
+// thread owns one support vector k, so its 49 values are one contiguous run of the row; corr_mlp.fc1 is multiplied with
+// a copy of its weights whose columns are permuted the same way (api.cu, Layout::corr_fc1_t).
 //
 // Correlate-then-interpolate like corr_tc2.cu (bilinear sampling is linear in the feature map, so the tensor cores
 // correlate the RAW 8x8 texel patch around the track with the 49 support vectors and the epilogue blends the 64 raw
@@ -202,16 +205,27 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int acc, int q
     float out[kP];
     yblend_dispatch(dy, hx, uy, wy, out);
     if (live) {
-      uint16_t* row = img + f * (ROW_BYTES / 2);
+      // support-major volume row: element k*49 + i (i = a*7 + b), i.e. this thread's 49 values are CONTIGUOUS: one
+      // 2-byte edge element (the first if the offset is odd, else the last) + 24 aligned 4-byte pairs per plane
+      const bool odd = (k & 1) != 0;
+      uint16_t* dst = img + f * (ROW_BYTES / 2) + k * kP;
+      uint32_t* ph = reinterpret_cast<uint32_t*>(dst + (odd ? 1 : 0));
+      if (V16) {
 #pragma unroll
-      for (int i = 0; i < kP; ++i) {
-        if (V16) {
-          row[i * kP + k] = __half_as_ushort(__float2half_rn(out[i]));
-        } else {
-          const bf16pair sp = split_bf16(out[i]);
-          row[i * kP + k] = __bfloat16_as_ushort(sp.hi);
-          row[kVolPad + i * kP + k] = __bfloat16_as_ushort(sp.lo);
+        for (int j = 0; j < 24; ++j) ph[j] = pack_h2(odd ? out[2 * j + 1] : out[2 * j], odd ? out[2 * j + 2] : out[2 * j + 1]);
+        dst[odd ? 0 : 48] = __half_as_ushort(__float2half_rn(odd ? out[0] : out[48]));
+      } else {
+        uint32_t* pl = reinterpret_cast<uint32_t*>(dst + kVolPad + (odd ? 1 : 0));
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          uint32_t hi, lo;
+          split2(odd ? out[2 * j + 1] : out[2 * j], odd ? out[2 * j + 2] : out[2 * j + 1], hi, lo);
+          ph[j] = hi;
+          pl[j] = lo;
         }
+        const bf16pair ed = split_bf16(odd ? out[0] : out[48]);
+        dst[odd ? 0 : 48] = __bfloat16_as_ushort(ed.hi);
+        dst[kVolPad + (odd ? 0 : 48)] = __bfloat16_as_ushort(ed.lo);
       }
     }
   }

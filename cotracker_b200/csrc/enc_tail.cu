@@ -50,14 +50,18 @@ im2col3x3_split_kernel(const float* __restrict__ in, int T, int C, int H, int W,
   }
 }
 
-// per (t, channel) mean / rstd over the HW rows of an NHWC fp32 tensor [T*HW, C]; block = (t, 32 channels)
+// per (t, channel) mean / rstd over the HW rows of an NHWC fp32 tensor [T*HW, C], fp64 accumulation, deterministic:
+// stage 1: block (32-channel group, t, split) sums its share of the rows (8 row lanes x rows strided by 8 * splits)
+// into part[t][split][c][2]; stage 2: one thread per (t, c) adds the splits in order.  (A single block per (t, 32
+// channels) left 32 blocks for the whole GPU on the 64-channel stages: 5.5 ms per step.)
+constexpr int kStatSplits = 32;
 __global__ void __launch_bounds__(256)
-instnorm_stats_kernel(const float* __restrict__ y, int HW, int C, float eps, float* __restrict__ stats /*[T,C,2]*/) {
-  const int t = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31);
+instnorm_partial_kernel(const float* __restrict__ y, int HW, int C, double* __restrict__ part /*[T,splits,C,2]*/) {
+  const int t = blockIdx.y, sp = blockIdx.z, c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r0 = threadIdx.x >> 5;   // 8 row lanes
   double s = 0.0, ss = 0.0;
   const float* base = y + (int64_t)t * HW * C + c;
-  for (int r = r0; r < HW; r += 8) {
+  for (int r = sp * 8 + r0; r < HW; r += 8 * kStatSplits) {
     const float v = base[(int64_t)r * C];
     s += v;
     ss += (double)v * v;
@@ -68,11 +72,26 @@ instnorm_stats_kernel(const float* __restrict__ y, int HW, int C, float eps, flo
   __syncthreads();
   if (r0 == 0) {
     for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x & 31]; ss += sh[1][i][threadIdx.x & 31]; }
-    const double mean = s / HW;
-    const double var = fmax(ss / HW - mean * mean, 0.0);
-    stats[((int64_t)t * C + c) * 2 + 0] = (float)mean;
-    stats[((int64_t)t * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    double* o = part + (((int64_t)t * kStatSplits + sp) * C + c) * 2;
+    o[0] = s;
+    o[1] = ss;
   }
+}
+__global__ void instnorm_finish_kernel(const double* __restrict__ part, int T, int HW, int C, float eps,
+                                       float* __restrict__ stats /*[T,C,2]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * C) return;
+  const int t = i / C, c = i % C;
+  double s = 0.0, ss = 0.0;
+  for (int sp = 0; sp < kStatSplits; ++sp) {
+    const double* p = part + (((int64_t)t * kStatSplits + sp) * C + c) * 2;
+    s += p[0];
+    ss += p[1];
+  }
+  const double mean = s / HW;
+  const double var = fmax(ss / HW - mean * mean, 0.0);
+  stats[(int64_t)i * 2 + 0] = (float)mean;
+  stats[(int64_t)i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // relu((y - mean) * rstd) -> split [rows, 2*C]; one thread = 4 channels of one row
@@ -167,9 +186,12 @@ cudaError_t launch_im2col3x3_split(const float* in, int T, int C, int H, int W, 
   im2col3x3_split_kernel<<<grid, 256, 0, s>>>(in, T, C, H, W, Kpad, out);
   return cudaGetLastError();
 }
-cudaError_t launch_instnorm_stats(const float* y, int T, int HW, int C, float eps, float* stats, cudaStream_t s) {
-  dim3 grid(C / 32, T);
-  instnorm_stats_kernel<<<grid, 256, 0, s>>>(y, HW, C, eps, stats);
+size_t instnorm_scratch_bytes(int T, int C) { return (size_t)T * kStatSplits * C * 2 * sizeof(double); }
+cudaError_t launch_instnorm_stats(const float* y, int T, int HW, int C, float eps, float* stats, void* scratch,
+                                  cudaStream_t s) {
+  dim3 grid(C / 32, T, kStatSplits);
+  instnorm_partial_kernel<<<grid, 256, 0, s>>>(y, HW, C, reinterpret_cast<double*>(scratch));
+  instnorm_finish_kernel<<<(T * C + 255) / 256, 256, 0, s>>>(reinterpret_cast<const double*>(scratch), T, HW, C, eps, stats);
   return cudaGetLastError();
 }
 cudaError_t launch_instnorm_relu_split(const float* y, const float* stats, int64_t rows, int HW, int C,

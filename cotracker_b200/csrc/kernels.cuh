@@ -22,7 +22,10 @@ cudaError_t launch_pyramid_pools(int T, int H4, int W4, float* pyr, cudaStream_t
 // ---- enc_tail.cu : conv2 -> InstanceNorm -> ReLU -> conv3 of the encoder on the GEMM engine --------
 cudaError_t launch_im2col3x3_split(const float* in, int T, int C, int H, int W, int Kpad, __nv_bfloat16* out,
                                    cudaStream_t s);
-cudaError_t launch_instnorm_stats(const float* y, int T, int HW, int C, float eps, float* stats, cudaStream_t s);
+// scratch: instnorm_scratch_bytes(T, C) bytes (fp64 partial sums of the two-stage reduction)
+size_t instnorm_scratch_bytes(int T, int C);
+cudaError_t launch_instnorm_stats(const float* y, int T, int HW, int C, float eps, float* stats, void* scratch,
+                                  cudaStream_t s);
 cudaError_t launch_instnorm_relu_split(const float* y, const float* stats, int64_t rows, int HW, int C,
                                        __nv_bfloat16* out, cudaStream_t s);
 cudaError_t launch_l2norm_rows(const float* in, int64_t rows, float* out, cudaStream_t s);
@@ -114,6 +117,10 @@ struct AttnParams {
   float scale;
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t s);   // exact-fp32 SIMT (verification)
+
+// ---- attention_p2v.cu : point <- virtual cross attention (Lk == 64 keys) on tcgen05 ----------------------------------
+bool attention_p2v_supported(const AttnParams& p);
+cudaError_t launch_attention_p2v(const AttnParams& p, cudaStream_t s);
 
 // ---- attention_tc.cu : tensor-core (mma.sync split-bf16x3) production path ------------------------
 constexpr int kAttnMaxSplits = 32;

@@ -161,7 +161,8 @@ __global__ void split_rows_kernel(const float* __restrict__ x, int rows, int K, 
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % Kpad);
     const int64_t r = idx / Kpad;
-    const int sc = perm_x ? x_src_col(c) : (c < K ? c : -1);
+    // perm_x: 1 = X column permutation, 2 = correlation-volume transpose (dst k*49 + i <- src i*49 + k)
+    const int sc = perm_x == 1 ? x_src_col(c) : (perm_x == 2 ? (c < kVol ? (c % kP) * kP + c / kP : -1) : (c < K ? c : -1));
     const float v = sc >= 0 ? x[r * K + sc] : 0.f;
     __nv_bfloat16* o = out + (dst_row_off + r) * (2 * (int64_t)Kpad) + c;
     if (fp16) {

@@ -35,6 +35,7 @@ def _declare(lib):
         "ct3_set_option": (c_int, [c_char_p, c_int]),
         "ct3_get_option": (c_int, [c_char_p, intp]),
         "ct3_precision_info": (c_int, [c_int, c_int, c_int, intp, intp, intp]),
+        "ct3_volume_is_support_major": (c_int, [c_int, c_int, c_int, intp]),
         "ct3_num_weight_tensors": (c_int, []),
         "ct3_weight_name": (c_char_p, [c_int]),
         "ct3_packed_weights_bytes": (c_int, [ctypes.POINTER(c_size_t)]),
@@ -74,7 +75,7 @@ def _declare(lib):
 
 
 EXPORTED_SYMBOLS = [
-    "ct3_version", "ct3_last_error", "ct3_set_option", "ct3_get_option", "ct3_precision_info", "ct3_num_weight_tensors",
+    "ct3_version", "ct3_last_error", "ct3_set_option", "ct3_get_option", "ct3_precision_info", "ct3_volume_is_support_major", "ct3_num_weight_tensors",
     "ct3_weight_name", "ct3_packed_weights_bytes", "ct3_pack_weights", "ct3_pyramid_layout",
     "ct3_prepare_pyramid", "ct3_sample_support", "ct3_workspace_bytes", "ct3_update_loop",
     "ct3_corr_sample", "ct3_linear", "ct3_linear_prec", "ct3_split_rows", "ct3_split_rows_fp16", "ct3_updateformer", "ct3_profile_enable", "ct3_profile_read",
@@ -282,7 +283,12 @@ def corr_sample(pyr, H4, W4, support, track_valid, coords, scratch: bool = True)
         v = vol.float()
         full = v[:, :VOL_PAD] + v[:, VOL_PAD:]
     assert bool((full[:, VOL:] == 0).all()), "K padding of the correlation volume must be zero"
-    return full[:, :VOL].reshape(N, T, LEVELS, VOL)
+    full = full[:, :VOL]
+    flag = ctypes.c_int(0)
+    _check(lib().ct3_volume_is_support_major(T, H4, W4, ctypes.byref(flag)), "ct3_volume_is_support_major")
+    if scratch and flag.value:   # corr_tc3.cu: rows are [k][a*7+b]; hand back the reference order [(a*7+b)][k]
+        full = full.reshape(-1, P, P).transpose(1, 2).reshape(-1, VOL)
+    return full.reshape(N, T, LEVELS, VOL)
 
 
 def split_rows(x: torch.Tensor, Kpad: int, fp16: bool = False) -> torch.Tensor:

@@ -81,6 +81,10 @@ int ct3_get_option(const char* name, int* value);
  * products of the 49x128x49 correlation contraction (cotracker3_offline.py:148-156), of corr_mlp.fc1
  * (blocks.py:61), and the bytes per element of the correlation volume (4 = split bf16 hi|lo, 2 = one fp16 plane). */
 int ct3_precision_info(int T, int H4, int W4, int* corr_products, int* fc1_products, int* volume_bytes_per_element);
+/* 1 when ct3_corr_sample / the update loop emit volume rows support-major (element k*49 + (a*7+b): corr_tc3.cu, the
+ * default kernel) instead of the reference's sample-major (a*7+b)*49 + k (cotracker3_offline.py:148-156); the matching
+ * column permutation of corr_mlp.fc1 is applied at pack time, so this only matters to callers of the stage API. */
+int ct3_volume_is_support_major(int T, int H4, int W4, int* flag);
 
 /* ---- one-time weight packing ------------------------------------------------
  * Replaces the nn.Module parameter storage read by cotracker3_online.py:73-92.

@@ -219,8 +219,10 @@ def test_updateformer_stage(eng, impl):
     assert err < 2e-4 * max(scale, 1.0), (err, scale)
 
 
-@pytest.mark.parametrize("attn", [0, 1])   # 0: tensor-core flash kernel (product), 1: exact-fp32 SIMT cross-check
-@pytest.mark.parametrize("N,T", [(70, 6), (600, 20), (130, 40), (1030, 16)])
+# 0: product kernels (fused tcgen05 time attention, mma.sync kernels for the space patterns),
+# 1: exact-fp32 SIMT cross-check, 2: like 0 with the tcgen05 point<-virtual attention kernel (attention_p2v.cu)
+@pytest.mark.parametrize("attn", [0, 1, 2])
+@pytest.mark.parametrize("N,T", [(70, 6), (600, 20), (130, 40), (1030, 16), (129, 5), (3, 2)])
 def test_updateformer_attention_shapes(eng, attn, N, T):
     """Exercises every attention variant: per-warp time attention with KB=16/32/64, shared K/V, split-K + combine
     (N >= 512 keys), ragged query/key tails."""
