@@ -10,7 +10,7 @@
 //      written as the K-major A tile of the second product (64 keys = exactly one 128-byte row)
 //   4. O = P V : M=128, N=48, 4 k16 steps x 3 split products -> TMEM -> registers -> split bf16 rows of the
 //      out-projection's operand buffer
-// Two CTAs are resident per SM (92 KiB of shared memory, 128 TMEM columns each) and hide each other's phase latency.
+// Three CTAs are resident per SM (65 KiB of shared memory, 128 TMEM columns each) and hide each other's phase latency.
 // Replaces the mma.sync kernel of attention_tc.cu for this pattern (190 us -> see profiles/ per call at N=6400, T=16).
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -24,14 +24,14 @@ constexpr int PV_TILE_K = 64 * 128;      // [64 keys x 128 B] one plane of K
 constexpr int PV_OFF_Q = 0;                              // hi | lo
 constexpr int PV_OFF_K = PV_OFF_Q + 2 * PV_TILE_Q;       // hi | lo
 constexpr int PV_OFF_V = PV_OFF_K + 2 * PV_TILE_K;       // hi | lo (each padded to 8 KiB for 1024-byte alignment)
-constexpr int PV_OFF_P = PV_OFF_V + 2 * 8192;            // hi | lo
-constexpr int PV_OFF_BAR = PV_OFF_P + 2 * PV_TILE_Q;
+constexpr int PV_OFF_P = PV_OFF_Q;                       // P reuses the Q tiles (S = Q K^T has retired when P is written)
+constexpr int PV_OFF_BAR = PV_OFF_V + 2 * 8192;
 constexpr int PV_SMEM = PV_OFF_BAR + 64 + 1024;
-static_assert(PV_SMEM <= 113 * 1024, "two CTAs per SM");
+static_assert(PV_SMEM <= 75 * 1024, "three CTAs per SM");
 
 __device__ __forceinline__ uint32_t swz(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
-__global__ void __launch_bounds__(PV_THREADS, 2)
+__global__ void __launch_bounds__(PV_THREADS, 3)
 attn_p2v_tc_kernel(AttnParams p, int tiles_per_seq) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
@@ -73,9 +73,9 @@ attn_p2v_tc_kernel(AttnParams p, int tiles_per_seq) {
     {
       const float4* q4 = reinterpret_cast<const float4*>(qrow + h * kDh);
 #pragma unroll
-      for (int c = 0; c < kDh / 8; ++c) {          // 6 chunks of 8 elements = 16 bytes per plane
+      for (int c = 0; c < 8; ++c) {                // 6 chunks of 8 elements = 16 bytes per plane + 2 chunks of zero padding
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (valid) { a = __ldg(q4 + 2 * c); b = __ldg(q4 + 2 * c + 1); }
+        if (valid && c < kDh / 8) { a = __ldg(q4 + 2 * c); b = __ldg(q4 + 2 * c + 1); }
         uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
         split2(a.x * qscale, a.y * qscale, h0, l0);
         split2(a.z * qscale, a.w * qscale, h1, l1);

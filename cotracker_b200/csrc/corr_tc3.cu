@@ -17,7 +17,7 @@
 //   pyramid  : ONE fp16 plane per level [T][H][W][128] (made once per update-loop call); texels are rounded to fp16
 //              (2^-12 relative), the support vectors are exact to a split fp16 pair (prec.corr = 2)
 //   B tile   [128 texel rows x 64 ch] : rows f*64 + y*8 + x = the raw texels of 2 frames; each (frame, K-half) is ONE
-//              4-D TMA box (64 ch x 8 x 8 x 1) landing in the 128B-swizzled K-major operand layout; ring of 6 K-half
+//              4-D TMA box (64 ch x 8 x 8 x 1) landing in the 128B-swizzled K-major operand layout; ring of 5 K-half
 //              slots (16 KiB), each freed as soon as its MMAs retire
 //   A tiles  4 x [128 x 64 ch] : {hi, lo} plane x K-half of the 49 support vectors of (n,l) in rows 0..48 (rows 49..127
 //              stay zero), built once per unit by 2 warps.  The hi and lo planes are CONCATENATED ALONG K:
@@ -25,7 +25,9 @@
 //              holds the complete (S_hi + S_lo)[k] . F and the epilogue needs no exchange between warps.
 //              (prec.corr = 1 skips the lo MMAs: single fp16 product.)
 //   D        [128 x 128] fp32 in TMEM, lanes 0..48 live, columns = texels (f*64 + y*8 + x); 4 accumulators
-//   epilogue : 3 groups x 2 warps (TMEM lane quarters 0 and 1) take tiles round-robin; thread = support vector k.
+//   epilogue : 4 groups x 2 warps (TMEM lane quarters 0 and 1) take tiles round-robin; thread = support vector k.
+//              (Each epilogue warp is a latency-bound dependent chain -- ~0.2 IPC -- so throughput comes from the number
+//              of groups: 128 registers per thread buy the fourth one.)
 //              Per frame: 4 x tcgen05.ld (two texel rows each) -> x-blend -> y-blend -> 49 sampled correlations ->
 //              convert -> volume-row image in shared memory -> bulk shared->global copy of the whole 9.5 KiB row.
 //              A border clamp only turns the tap indices into a clamped SHIFT of the interior pattern
@@ -36,8 +38,8 @@
 //              otherwise idle lanes of the TMA warp.  The blend code exists ONCE (frame loop not unrolled): a fully
 //              unrolled epilogue is 290 KB of SASS and ran 5x slower on instruction-cache misses
 //              (profiles/r2_corr_tc3_history.txt).
-// Warps (10): 0,1 / 4,5 / 8,9 epilogue groups (warp % 4 = TMEM lane quarter), 2 TMA issuer (+ tap tables), 3 MMA issuer
-// (+ TMEM alloc), 6,7 support builders.
+// Warps (14): 0,1 / 4,5 / 8,9 / 12,13 epilogue groups (warp % 4 = TMEM lane quarter), 2 TMA issuer (+ tap tables),
+// 3 MMA issuer (+ TMEM alloc), 6,7 support builders, 10,11 idle.
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -47,9 +49,9 @@ namespace {
 constexpr int TMA_WARP = 2;
 constexpr int MMA_WARP = 3;
 constexpr int SB_WARP0 = 6;               // warps 6, 7 build the support operand
-constexpr int NGROUP = 3;                 // epilogue groups: warps {0,1}, {4,5}, {8,9}
-constexpr int THREADS = 10 * 32;
-constexpr int NSLOT = 6;                  // texel ring: slots of one K-half (64 channels) of a 2-frame tile
+constexpr int NGROUP = 4;                 // epilogue groups: warps {0,1}, {4,5}, {8,9}, {12,13}  (warps 10, 11 idle)
+constexpr int THREADS = 14 * 32;          // 128 registers per thread
+constexpr int NSLOT = 5;                  // texel ring: slots of one K-half (64 channels) of a 2-frame tile
 constexpr int A_SLOT = 16384;             // [128 texel rows x 128 B] fp16
 constexpr int S_TILE = 16384;             // one (plane, K-half) of S: [128 rows x 128 B], rows 49..127 zero
 constexpr int S_BYTES = 4 * S_TILE;       // tile index = plane * 2 + K-half
@@ -304,7 +306,7 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
           box_origin8(cx1, W, bx1, dx1);
           box_origin8(cy1, H, by1, dy1);
           // The first K-half slot of this tile doubles as the gate of the table slot: slot it % 8 was last used by
-          // tile it - 8; the ring slot waited for here was freed by the MMAs of tile it - 3, which were issued after
+          // tile it - 8; the ring slot waited for here was freed by MMAs of tile it - 3, which were issued after
           // tile it - 4's, which needed the accumulator that tile it - 8's epilogue had released after reading its table.
           mbar_wait_spin(&a_empty[hc % NSLOT], ((hc / NSLOT) & 1u) ^ 1u);
           {
@@ -414,8 +416,8 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(s_full);
     }
-  } else {
-    // ================================================================== epilogue: warps {0,1}, {4,5}, {8,9}
+  } else if ((warp & 3) < 2) {
+    // ================================================================== epilogue: warps {0,1}, {4,5}, {8,9}, {12,13}
     const int grp = warp >> 2;                 // tiles with it % NGROUP == grp
     const int q = warp & 3;                    // TMEM lane quarter 0 or 1
     uint16_t* img = reinterpret_cast<uint16_t*>(smem + OFF_IMG + grp * IMG_GROUP);

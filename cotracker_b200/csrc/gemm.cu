@@ -450,20 +450,22 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 // track-major (row = n*T + t): a tile starts at row mt*R with R = floor(128 / T) * T, i.e. it owns whole tracks
 // (the MMA still multiplies 128 rows; the rows past R belong to the next tile and are ignored).
 // cta_group::2 pairs as in gemm_split3_pair_kernel (256-row MMA, each CTA loads its 128 rows of X and 72 of the 144
-// weight rows).  Epilogue, per CTA on its own 128 rows: 8 warps = 2 groups x 4 TMEM lane quarters;
-//   group 1     : tcgen05.ld the k and v columns, + bias, -> shared [row][k 48 | v 48] fp32
-//   group 0     : tcgen05.ld the q columns (+ bias) into registers, then -- after a named barrier -- exact fp32
-//                 online-softmax attention of its row against the T key rows of its track in shared memory, and
-//                 writes the 48 outputs as split bf16 straight into the out-projection's operand buffer.
+// weight rows).  Epilogue, per CTA on its own 128 rows: 2 independent groups of 4 warps (TMEM lane quarters) take
+// alternate tiles (group g owns accumulator g and its own K/V buffer), so two tiles are in their epilogue at once.
+// Per tile a thread (= row) reads q (+ bias) into registers, writes k and v (+ bias) to shared [row][k 48 | v 48] fp32,
+// releases the accumulator, and -- after the group's named barrier -- runs exact fp32 online-softmax attention of its
+// row against the T key rows of its track, then writes the 48 outputs as split bf16 straight into the
+// out-projection's operand buffer.
 // The fp32 q|k|v tensor (4.6 KB per token) never reaches HBM and the separate attention launch disappears.
 namespace qa {
 constexpr int BNQ = 144;                               // q|k|v of one head
 constexpr int TILE_BQ = (BNQ / 2) * BK * 2;            // 9216 B: this CTA's 72 weight rows, one plane
 constexpr int STAGE = 2 * TILE_A + 2 * TILE_BQ;        // 51200 B
-constexpr int NSTAGE = 3;
-constexpr int KV_LD = 100;                             // floats per row of the K/V buffer (96 + 4: conflict-free float4)
-constexpr int OFF_KV = NSTAGE * STAGE;                 // 153600
-constexpr int OFF_BARQ = OFF_KV + BM * KV_LD * 4;      // + 51200
+constexpr int NSTAGE = 2;                              // the kernel is epilogue-bound: a shallow ring buys the second K/V buffer
+constexpr int KV_LD = 100;                             // floats per row of a K/V buffer (96 + 4: conflict-free float4)
+constexpr int KV_BYTES = BM * KV_LD * 4;               // 51200 per epilogue group
+constexpr int OFF_KV = NSTAGE * STAGE;                 // 102400
+constexpr int OFF_BARQ = OFF_KV + 2 * KV_BYTES;        // + 102400
 constexpr int SMEM = OFF_BARQ + 256 + 1024;
 constexpr int EPIW = 8;
 constexpr int NTHREADS = (2 + EPIW) * 32;              // 320 threads (10 warps): up to 168 registers per thread
@@ -496,7 +498,7 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
     for (int i = 0; i < ACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * EPIW);
+      mbar_init(&tempty_bar[i], 2 * 4);        // one epilogue group (4 warps) per CTA of the pair
     }
     fence_barrier_init();
   }
@@ -563,14 +565,18 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
   } else {
     const int quarter = warp & 3;
-    const int group = (warp - 2) >> 2;             // 0: q + attention, 1: k and v -> shared memory
+    const int group = (warp - 2) >> 2;             // tiles alternate between the two groups; group g <-> accumulator g
     const int r = quarter * 32 + lane;             // row of the tile = TMEM lane
     const int tracks = R / T;
     const int jtrack = min(r / T, tracks - 1);     // rows past R are computed on a clamped track and never stored
-    const float* kbase = kvs + (int64_t)jtrack * T * KV_LD;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = first; tile < num_tiles; tile += step) {
+    float* kvg = kvs + group * (KV_BYTES / 4);
+    const float* kbase = kvg + (int64_t)jtrack * T * KV_LD;
+    const int bar_id = 1 + group;
+    int it = 0;
+    for (int tile = first; tile < num_tiles; tile += step, ++it) {
+      if ((it & 1) != group) continue;
+      const int acc = group;
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int mt = (tile / kHeads) * 2 + (int)rank, h = tile % kHeads;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after_sync();
@@ -580,12 +586,13 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         const int64_t grow_ln = (int64_t)mt * R + r;
         if (epi.ln_part && grow_ln < M) ln_row_stats(epi.ln_part + grow_ln * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
       }
-      float x[kDh];
-      // part 0 = q (group 0) or k (group 1); part 1 = v (group 1 only)
+      float xq[kDh];
+      // k, v -> shared memory first, q (kept in registers for the attention) last
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        if (part == 1 && group == 0) break;
-        const int col0 = (group == 0) ? 0 : kDh * (1 + part);
+      for (int pi = 0; pi < 3; ++pi) {
+        const int part = (pi + 1) % 3;   // 1 = k, 2 = v, 0 = q
+        float x[kDh];
+        const int col0 = kDh * part;
 #pragma unroll
         for (int c = 0; c < kDh / 16; ++c) {
           float v[16];
@@ -607,8 +614,11 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
             x[16 * c + 4 * i + 2] = v[4 * i + 2] + b.z; x[16 * c + 4 * i + 3] = v[4 * i + 3] + b.w;
           }
         }
-        if (group != 0) {
-          float4* dst = reinterpret_cast<float4*>(kvs + r * KV_LD + part * kDh);
+        if (part == 0) {
+#pragma unroll
+          for (int i = 0; i < kDh; ++i) xq[i] = x[i];
+        } else {
+          float4* dst = reinterpret_cast<float4*>(kvg + r * KV_LD + (part - 1) * kDh);
 #pragma unroll
           for (int i = 0; i < kDh / 4; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
         }
@@ -616,9 +626,8 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);   // accumulator drained (leader's barrier)
-      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // K/V of this tile are in shared memory
-      if (group == 0) {
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // K/V of this tile are in shared memory
+      {
         float m = -INFINITY, l = 0.f;
         float o[kDh];
 #pragma unroll
@@ -632,10 +641,10 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 kk = *reinterpret_cast<const float4*>(kbase + min(t0 + i, T - 1) * KV_LD + 4 * d4);
-              sc[i] = fmaf(x[4 * d4 + 0], kk.x, sc[i]);
-              sc[i] = fmaf(x[4 * d4 + 1], kk.y, sc[i]);
-              sc[i] = fmaf(x[4 * d4 + 2], kk.z, sc[i]);
-              sc[i] = fmaf(x[4 * d4 + 3], kk.w, sc[i]);
+              sc[i] = fmaf(xq[4 * d4 + 0], kk.x, sc[i]);
+              sc[i] = fmaf(xq[4 * d4 + 1], kk.y, sc[i]);
+              sc[i] = fmaf(xq[4 * d4 + 2], kk.z, sc[i]);
+              sc[i] = fmaf(xq[4 * d4 + 3], kk.w, sc[i]);
             }
           }
           float mnew = m;
@@ -679,7 +688,7 @@ gemm_qkv_time_attn_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
           }
         }
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");   // K/V consumed: the next tile may overwrite the buffer
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // K/V consumed: this group's next tile may overwrite
     }
   }
 
