@@ -121,6 +121,7 @@ __device__ __forceinline__ void xblend(const float (&v)[64], const float (&u)[7]
 }
 __device__ __forceinline__ void xblend_dispatch(int d, const float (&v)[64], const float (&u)[7], const float (&w)[7],
                                                 float (&hx)[8][7]) {
+  if (d == 0) { xblend<0>(v, u, w, hx); return; }   // interior tiles (the majority): a direct branch, no jump table
   switch (d) {   // warp-uniform
     case -7: xblend<-7>(v, u, w, hx); break;
     case -6: xblend<-6>(v, u, w, hx); break;
@@ -149,6 +150,7 @@ __device__ __forceinline__ void yblend(const float (&hx)[8][7], const float (&u)
 }
 __device__ __forceinline__ void yblend_dispatch(int d, const float (&hx)[8][7], const float (&u)[7], const float (&w)[7],
                                                 float (&out)[kP]) {
+  if (d == 0) { yblend<0>(hx, u, w, out); return; }
   switch (d) {
     case -7: yblend<-7>(hx, u, w, out); break;
     case -6: yblend<-6>(hx, u, w, out); break;

@@ -5,10 +5,12 @@ gpu__time_duration.sum, dram__bytes_read.sum and dram__bytes_write.sum:
 import csv, json, sys
 from collections import defaultdict
 
-FAMILIES = [("corr_sample", ("corr_sample_tc_kernel", "corr_patch_tc_kernel", "corr_sample_simt_kernel")),
-            ("gemm", ("gemm_split3",)),
+FAMILIES = [("corr_sample", ("corr_sample_tc_kernel", "corr_patch_tc_kernel", "corr_patch_t_kernel", "corr_sample_simt_kernel")),
+            ("encoder", ("conv3x3_tc_kernel", "conv_stem_kernel", "norm_act_kernel", "instnorm_", "gather_s2_kernel",
+                         "upsample_concat", "l2norm_rows", "avgpool2")),
+            ("gemm", ("gemm_split3", "gemm_qkv_time_attn")),
             ("layernorm", ("layernorm_split_kernel",)),
-            ("attention", ("attention_tc_kernel", "attention_combine_kernel", "attention_simt"))]
+            ("attention", ("attention_tc_kernel", "attention_combine_kernel", "attention_simt", "attn_p2v"))]
 BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 SECS = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 

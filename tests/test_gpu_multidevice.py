@@ -22,16 +22,32 @@ def test_second_device_after_first():
 
 @needs2
 def test_two_host_threads_two_devices():
+    """Two host threads, each driving its own GPU through the same library at the same time.  Weights and inputs are
+    built in the main thread (seeded_state_dict seeds torch's GLOBAL generator, which two threads would race on);
+    the threads only run the predictor -- concurrently, several times -- and every result must match the golden."""
+    from cotracker_b200.predictor import CoTrackerPredictor
+    from oracle.make_golden import case_inputs, predictor_kwargs
+    name = "c2_grid30_stress"
+    cfg = CASES[name]
+    sd, video, queries = case_inputs(cfg)
+    want = load_golden(name)
+    jobs = []
+    for i in range(2):
+        p = CoTrackerPredictor(checkpoint=None, window_len=cfg["window_len"])
+        p.model.load_state_dict(sd)
+        jobs.append((p.to(f"cuda:{i}"), video.to(f"cuda:{i}")))
     errs = []
 
-    def work(dev):
+    def work(p, v):
         try:
-            for _ in range(2):
-                compare(run_cuda("c2_grid30_stress", device=dev), load_golden("c2_grid30_stress"))
+            for _ in range(3):
+                with torch.no_grad():
+                    tr, vi = p(v, **predictor_kwargs(cfg, v, queries))
+                compare(dict(tracks=tr.cpu(), visibility=vi.cpu()), want)
         except Exception as e:  # noqa: BLE001
-            errs.append((dev, repr(e)))
+            errs.append((str(v.device), repr(e)))
 
-    ts = [threading.Thread(target=work, args=(f"cuda:{i}",)) for i in range(2)]
+    ts = [threading.Thread(target=work, args=j) for j in jobs]
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
