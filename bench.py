@@ -372,6 +372,10 @@ def main():
     corr_bytes = ITERS * (Tw * 16320 * 128 * 4 + N * 4 * 49 * 128 * 4 + Tw * N * 8 + Tw * N * 4 * 2401 * vol_bytes)
     corr_gbs = corr_bytes / (cat_ms["corr_sample"] / 1e3) / 1e9 if cat_ms["corr_sample"] > 0 else 0.0
     lib_ms = sum(cat_ms.values())
+    # the fused q|k|v projection + time attention kernel: its projection FLOPs over its own time (3 blocks x ITERS calls)
+    Tw_rows = (N + 64) * Tw
+    qkva_tflops = (ITERS * 3 * 2.0 * Tw_rows * 1152 * 384) / (cat_ms["qkv_time_attention"] / 1e3) / 1e12 \
+        if cat_ms.get("qkv_time_attention", 0) > 0 else 0.0
 
     line = {
         "metric": METRIC if not online else "tracked points*new frames/sec, cotracker3_online, 512^2 stream, step 8",
@@ -399,6 +403,12 @@ def main():
                           "traffic_source": traffic_src,
                           "algorithmic_bytes_per_step": corr_bytes, "volume_bytes_per_element": vol_bytes,
                           "ms_per_step": cat_ms["corr_sample"], "launches_per_step": cat_n["corr_sample"]},
+        "roofline_qkv_attention": {"kernel": "gemm_qkv_time_attn_kernel (q|k|v projection + per-track time attention, one "
+                                             "kernel)", "bound": "tensor", "achieved": qkva_tflops, "peak": pk["bf16"],
+                                   "unit": "TFLOP/s", "frac": qkva_tflops / pk["bf16"],
+                                   "note": "projection FLOPs only (the T x T attention runs as fp32 FMA in the epilogue); "
+                                           "ncu tensor-pipe active 52 % (profiles/r2_ncu_qkv_time_attn.txt)",
+                                   "ms_per_step": cat_ms.get("qkv_time_attention", 0.0)},
         "kernel_ms_per_step": cat_ms, "library_ms_per_step": lib_ms,
     }
 

@@ -71,7 +71,7 @@ int num_sms() {   // of the CURRENT device (one process may drive several GPUs)
 
 // ------------------------------------------------------------------------------------------------
 // optional live profiler: CUDA events around every launch, summed per kernel category (bench.py roofline)
-enum { CAT_CORR = 0, CAT_GEMM = 1, CAT_ATTN = 2, CAT_LN = 3, CAT_MISC = 4, CAT_ENC = 5, CAT_COUNT = 6 };
+enum { CAT_CORR = 0, CAT_GEMM = 1, CAT_ATTN = 2, CAT_LN = 3, CAT_MISC = 4, CAT_ENC = 5, CAT_QKVA = 6, CAT_COUNT = 7 };
 struct ProfRec { int cat; cudaEvent_t a, b; double flops; int launches; };
 thread_local bool g_prof_on = false;
 thread_local std::vector<ProfRec> g_prof;
@@ -330,7 +330,7 @@ int transformer_body(Runner& R, const Workspace& W, int T, int N) {
       RUNC(CAT_LN, launch_layernorm_split(W.tokens, Rall, nullptr, nullptr, 1e-6f, W.ln, R.s));
       if (g_opt[OPT_FUSE] >= 1 && R.impl == 0 && g_opt_attn != 1 && qkv_time_attn_supported(T)) {
         // q|k|v projection and the per-track T x T attention in ONE kernel: fp32 q|k|v never reaches HBM
-        ProfScope ps(R.s, CAT_GEMM, 2.0 * (double)Rall * 3 * kC * kC);
+        ProfScope ps(R.s, CAT_QKVA, 0.0);
         int rc = gemm_qkv_time_attn_launch(W.ln, reinterpret_cast<const __nv_bfloat16*>(pk + b.qkv_h.w),
                                            reinterpret_cast<const float*>(pk + b.qkv_h.b), Rall, kC, T, W.att, 2 * kC,
                                            kC, scale, nullptr, nullptr, 0.f, num_sms(), R.s, &R.gerr);
@@ -477,7 +477,7 @@ int transformer_body_fold(Runner& R, const Workspace& W, int T, int N) {
     {  // ---- time block (cotracker.py:494-495)
       const Block& b = L.time[i];
       {
-        ProfScope ps(R.s, CAT_GEMM, 2.0 * (double)Rall * 3 * kC * kC);
+        ProfScope ps(R.s, CAT_QKVA, 0.0);
         int rc = gemm_qkv_time_attn_launch(W.traw, reinterpret_cast<const __nv_bfloat16*>(pk + b.qkv_h.w),
                                            reinterpret_cast<const float*>(pk + b.qkv_h.b), Rall, kC, T, W.att, 2 * kC,
                                            kC, scale, W.tstat, reinterpret_cast<const float*>(pk + b.qkv_h.ws), 1e-6f,
@@ -695,7 +695,7 @@ int ct3_profile_enable(int on) {
   g_prof_on = on != 0;
   return 0;
 }
-// ms[6], launches[6], gemm_flops: sums since ct3_profile_enable(1); synchronises the recorded events
+// ms[7], launches[7], gemm_flops (plain linear layers only; category 6 = the fused q|k|v + time-attention kernel): sums since ct3_profile_enable(1); synchronises the recorded events
 int ct3_profile_read(double* ms, int* launches, double* gemm_flops) {
   if (!ms || !launches || !gemm_flops) return fail(CT3_EINVAL, "null argument%s");
   for (int i = 0; i < CAT_COUNT; ++i) { ms[i] = 0.0; launches[i] = 0; }
@@ -706,7 +706,7 @@ int ct3_profile_read(double* ms, int* launches, double* gemm_flops) {
     CK(cudaEventElapsedTime(&t, r.a, r.b), "profile elapsed");
     ms[r.cat] += t;
     launches[r.cat] += r.launches;
-    *gemm_flops += r.flops;
+    if (r.cat == CAT_GEMM) *gemm_flops += r.flops;
   }
   return 0;
 }

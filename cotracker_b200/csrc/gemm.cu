@@ -27,15 +27,19 @@ constexpr int MAX_STAGES = 6;
 //   3: A hi|lo, W hi|lo (64 KiB x 3)   2: A hi, W hi|lo (48 KiB x 4)   1: A hi, W hi (32 KiB x 6)
 template <int NPROD>
 struct Cfg {
-  static constexpr int AP = NPROD == 3 ? 2 : 1;
+  // NPROD == 4 / 5: 3 products + the LayerNorm-producer epilogue (raw split rows + partial statistics) / the
+  // LayerNorm-consumer epilogue -- separate instantiations so that the default kernels do not carry their registers
+  // (compiled into every kernel they cost each GEMM 20-64 bytes of spills and ~7 % of its time)
+  static constexpr int AP = NPROD >= 3 ? 2 : 1;
   static constexpr int BP = NPROD >= 2 ? 2 : 1;
   static constexpr int STAGE_BYTES = AP * TILE_A + BP * TILE_B;
-  static constexpr int STAGES = NPROD == 3 ? 3 : (NPROD == 2 ? 4 : 6);
+  static constexpr int STAGES = NPROD >= 3 ? 3 : (NPROD == 2 ? 4 : 6);
   static constexpr int OFF_B = AP * TILE_A;
 };
 constexpr int OFF_STG = 3 * 65536;                     // = STAGES * STAGE_BYTES of every variant
 static_assert(Cfg<1>::STAGES * Cfg<1>::STAGE_BYTES == OFF_STG && Cfg<2>::STAGES * Cfg<2>::STAGE_BYTES == OFF_STG &&
-              Cfg<3>::STAGES * Cfg<3>::STAGE_BYTES == OFF_STG, "ring size");
+              Cfg<3>::STAGES * Cfg<3>::STAGE_BYTES == OFF_STG && Cfg<4>::STAGES * Cfg<4>::STAGE_BYTES == OFF_STG &&
+              Cfg<5>::STAGES * Cfg<5>::STAGE_BYTES == OFF_STG, "ring size");
 constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_WORDS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 /*barriers*/ + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -55,10 +59,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // of global memory in whole 32-byte sectors.
 __device__ __forceinline__ int stg_idx(int row, int word) { return row * CW + ((word + (row >> 1)) & (CW - 1)); }
 
+template <bool PROD, bool CONS>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int N, int row0, int col0, int lane,
                                                float (&v)[CW], uint32_t* stg, float ln_mean = 0.f, float ln_rstd = 1.f) {
   const int row = row0 + lane;
-  if (e.ln_part) {   // LayerNorm of the A rows applied after the contraction (see GemmEpilogue)
+  if constexpr (CONS) {   // LayerNorm of the A rows applied after the contraction (see GemmEpilogue)
     const float4* w4 = reinterpret_cast<const float4*>(e.ln_wsum + col0);
 #pragma unroll
     for (int i = 0; i < CW / 4; ++i) {
@@ -112,7 +117,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, int M, int
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (row0 + 8 * k + rsub < M) *reinterpret_cast<float4*>(base + k * rstep) = x[k];
-    if (e.raw_split) {
+    if constexpr (PROD) {
       // the final rows once more as a split-bf16 operand + the partial LayerNorm statistics of this 16-column chunk
       const int chunk = col0 >> 4;
 #pragma unroll
@@ -243,7 +248,7 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const uint32_t koff = kk * 32;  // 16 elements = 32 bytes inside the 128-byte swizzle atom
             const uint64_t dah = umma_desc_sw128(a_hi + koff), dbh = umma_desc_sw128(b_hi + koff);
             const uint32_t first = (kb | kk) != 0 ? 1u : 0u;
-            if (NPROD == 3) {   // small terms first
+            if (NPROD >= 3) {   // small terms first
               umma_bf16(d_tmem, umma_desc_sw128(a_lo + koff), dbh, idesc, first);
               umma_bf16(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, 1u);
               umma_bf16(d_tmem, dah, dbh, idesc, 1u);
@@ -275,13 +280,15 @@ gemm_split3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const int row0 = mt * BM + quarter * 32;
       uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (epi.ln_part && row0 + lane < M) ln_row_stats(epi.ln_part + (int64_t)(row0 + lane) * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
+      if constexpr (NPROD == 5) {
+        if (row0 + lane < M) ln_row_stats(epi.ln_part + (int64_t)(row0 + lane) * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
+      }
 #pragma unroll 1
       for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
         float v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + chunk * CW);
         tmem_ld16(taddr, v);
-        epilogue_chunk(epi, M, N, row0, nt * BN + chunk * CW, lane, v, stg, ln_mean, ln_rstd);
+        epilogue_chunk<NPROD == 4, NPROD == 5>(epi, M, N, row0, nt * BN + chunk * CW, lane, v, stg, ln_mean, ln_rstd);
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty_bar[acc]);
@@ -388,7 +395,7 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             const uint32_t koff = kk * 32;
             const uint64_t dah = umma_desc_sw128(a_hi + koff), dbh = umma_desc_sw128(b_hi + koff);
             const uint32_t first = (kb | kk) != 0 ? 1u : 0u;
-            if (NPROD == 3) {
+            if (NPROD >= 3) {
               umma_bf16_2sm(d_tmem, umma_desc_sw128(a_lo + koff), dbh, idesc, first);
               umma_bf16_2sm(d_tmem, dah, umma_desc_sw128(b_lo + koff), idesc, 1u);
               umma_bf16_2sm(d_tmem, dah, dbh, idesc, 1u);
@@ -420,13 +427,15 @@ gemm_split3_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       const int row0 = mt * BM + quarter * 32;
       uint32_t* stg = reinterpret_cast<uint32_t*>(smem + OFF_STG) + (warp - 2) * STG_WORDS;
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (epi.ln_part && row0 + lane < M) ln_row_stats(epi.ln_part + (int64_t)(row0 + lane) * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
+      if constexpr (NPROD == 5) {
+        if (row0 + lane < M) ln_row_stats(epi.ln_part + (int64_t)(row0 + lane) * kLnParts * 2, epi.ln_eps, ln_mean, ln_rstd);
+      }
 #pragma unroll 1
       for (int chunk = chunk0; chunk < chunk0 + CH; ++chunk) {
         float v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNP + chunk * CW);
         tmem_ld16(taddr, v);
-        epilogue_chunk(epi, M, N, row0, nt * BNP + chunk * CW, lane, v, stg, ln_mean, ln_rstd);
+        epilogue_chunk<NPROD == 4, NPROD == 5>(epi, M, N, row0, nt * BNP + chunk * CW, lane, v, stg, ln_mean, ln_rstd);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -961,13 +970,21 @@ int gemm_launch(const GemmProblem& p, int impl, int num_sms, cudaStream_t stream
   {
     cudaError_t e = once_per_device(attr_set, [&] {
       cudaError_t e = set_attrs<3>();
+      if (e == cudaSuccess) e = set_attrs<4>();
+      if (e == cudaSuccess) e = set_attrs<5>();
       if (e == cudaSuccess) e = set_attrs<2>();
       if (e == cudaSuccess) e = set_attrs<1>();
       return e;
     });
     if (e != cudaSuccess) { *err = "gemm: cudaFuncSetAttribute(max dynamic smem) failed"; return (int)e; }
   }
-  cudaError_t e = p.products == 3 ? launch_tc<3>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
+  if (p.epi.ln_part && (p.products != 3 || p.epi.raw_split)) {
+    *err = "gemm: the LayerNorm-consumer epilogue needs 3 products and cannot be combined with raw_split";
+    return (int)cudaErrorInvalidValue;
+  }
+  cudaError_t e = (p.products == 3 && p.epi.raw_split) ? launch_tc<4>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
+                : (p.products == 3 && p.epi.ln_part) ? launch_tc<5>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
+                : p.products == 3 ? launch_tc<3>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
                 : p.products == 2 ? launch_tc<2>(p, tmX, tmW, bnp, num_mt, num_sms, stream)
                                   : launch_tc<1>(p, tmX, tmW, bnp, num_mt, num_sms, stream);
   return (int)e;

@@ -331,7 +331,7 @@ def updateformer(packed, x: torch.Tensor, workspace: Optional[torch.Tensor] = No
     return delta
 
 
-PROFILE_CATEGORIES = ["corr_sample", "gemm", "attention", "layernorm", "misc", "encoder"]
+PROFILE_CATEGORIES = ["corr_sample", "gemm", "attention", "layernorm", "misc", "encoder", "qkv_time_attention"]
 
 
 def profile_enable(on: bool):

@@ -158,7 +158,7 @@ int ct3_update_loop(const void* packed, const float* pyr, int H4, int W4, const 
  * kernel category: 0 corr_sample, 1 gemm (tcgen05), 2 attention, 3 layernorm, 4 misc.
  * ct3_profile_enable(1) clears and starts recording; ct3_profile_read synchronises and sums. */
 int ct3_profile_enable(int on);
-int ct3_profile_read(double ms[6], int launches[6], double* gemm_flops);
+int ct3_profile_read(double ms[7], int launches[7], double* gemm_flops);
 
 /* ---- stage-level entry points (used by the parity tests and profiles) ------- */
 
