@@ -25,7 +25,8 @@ constexpr OptDef kOptDefs[OPT_COUNT] = {
     {"gemm", 0, 1},   // 0 tcgen05, 1 SIMT verification
     {"corr", 0, 3},   // 0 tcgen05 correlate-then-interpolate (corr_tc3.cu / corr_tc2.cu), 1 exact-fp32 SIMT, 2 corr_tc.cu,
                       // 3 correlate-then-interpolate with corr_tc2.cu for every precision mode (A/B)
-    {"attn", 0, 2},   // 0 tensor-core kernels, 1 exact-fp32 SIMT verification, 2 = 0 + tcgen05 point<-virtual attention (A/B)
+    {"attn", 0, 2},   // 0 tensor-core kernels (tcgen05 point<-virtual, mma.sync elsewhere), 1 exact-fp32 SIMT verification,
+                      // 2 = mma.sync for point<-virtual too (the kernel attention_p2v.cu replaced; A/B)
     // tensor-core products per FLOP of a GEMM group: 3 = split x split (hi*hi + lo*hi + hi*lo),
     // 2 = fp16 activation plane x split fp16 weights, 1 = single fp16 product.  Only the correlation branch has the
     // switch: SURVEY 7.3 measured that every transformer GEMM breaks the 1e-3 px budget with fewer than 3 products.
@@ -295,8 +296,8 @@ struct Runner {
 
 int run_attention(Runner& R, const Workspace& W, const AttnParams& a, bool per_warp) {
   if (g_opt_attn == 1) return (int)launch_attention(a, R.s);
-  // point <- virtual (64 keys per frame, thousands of queries): experimental tcgen05 kernel (attention_p2v.cu), opt-in
-  if (g_opt_attn == 2 && !per_warp && a.Lq > kV && attention_p2v_supported(a)) return (int)launch_attention_p2v(a, R.s);
+  // point <- virtual (64 keys per frame, thousands of queries): tcgen05 kernel with TMA row staging (attention_p2v.cu)
+  if (g_opt_attn == 0 && !per_warp && a.Lq > kV && attention_p2v_supported(a)) return (int)launch_attention_p2v(a, R.s);
   return (int)launch_attention_tc(a, per_warp, W.att_part, num_sms(), R.s);
 }
 

@@ -251,6 +251,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// tensor store shared -> global (rows outside the tensor are clipped); completion through bulk_commit / bulk_wait*
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, int c0, int c1, int c2, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // bulk asynchronous copy shared -> global (TMA engine, no LSU traffic); sizes/addresses multiples of 16 bytes.
 // The issuing thread must have the generic-proxy writes of the source ordered by fence.proxy.async + a barrier.
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -405,6 +418,12 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld tied to the 8 registers of an earlier tmem_ld8_nowait (nothing that reads them is hoisted above the wait)
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               ::"memory");
+}
 
 // whole warp: lane i reads 64 consecutive fp32 columns of TMEM lane (base_lane + i) with ONE load + ONE wait
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {

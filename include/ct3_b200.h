@@ -72,7 +72,8 @@ const char* ct3_last_error(void);
 
 /* Debug/verification options ("gemm", "corr", "attn": 0 = tensor-core path (default),
  * 1 = SIMT fp32 verification kernel used by the tests to cross-check; "corr" = 2 forces the
- * sample-then-correlate tensor-core kernel that otherwise only serves pyramids with a level below 8x8). */
+ * sample-then-correlate tensor-core kernel that otherwise only serves pyramids with a level below 8x8;
+ * "attn" = 2 runs the point<-virtual attention on the mma.sync kernel instead of the tcgen05 one, for A/B). */
 int ct3_set_option(const char* name, int value);
 int ct3_get_option(const char* name, int* value);
 /* Precision switches of the correlation branch ("prec.corr", "prec.fc1": tensor-core products per FLOP, 3 | 2 | 1;
