@@ -77,6 +77,7 @@ struct Corr3Args {
   const float* coords;         // [T, N, 2]
   int T, N;
   uint16_t* vol;               // [N*T*4, 2*kVolPad] split bf16, or [N*T*4, kVolPad] fp16 (V16)
+  int* unit_counter;           // zeroed before the launch: units beyond the first one per CTA are handed out dynamically
 };
 struct Corr3Maps {
   CUtensorMap m[kL];           // per level: fp16 dims (128, W, H, T), box (64, 8, 8, 1), 128B swizzle
@@ -257,6 +258,19 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
   uint64_t* s_full = bars + 2 * NSLOT + 2 * NACC;       // builders -> MMA, per unit  (count 2)
   uint64_t* s_empty = bars + 2 * NSLOT + 2 * NACC + 1;  // MMA -> builders, per unit  (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * NACC + 2);
+  // Unit queue.  A unit = (track n, level l) = T frames of one support operand; SMs differ by up to 10 % in speed on
+  // this kernel (distance to the L2 slices), so only the first unit of a CTA is static (blockIdx.x) and the others
+  // come from a global counter.  The first builder warp -- the role that runs furthest ahead -- draws the numbers and
+  // publishes them here in order; every other role reads entry ui when it gets there (an entry is rewritten 8 units
+  // later, no role lags that far).  -1 ends every role's loop.
+  volatile int* unit_q = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [8]
+  volatile int* unit_tail = unit_q + 8;                                    // number of published entries
+  auto unit_at = [&](uint32_t ui) -> int {
+    uint32_t spins = 0;
+    while (*unit_tail <= (int)ui) { if (++spins > (1u << 28)) asm volatile("trap;"); }
+    __threadfence_block();
+    return unit_q[ui & 7];
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_unit = (g.T + 1) / 2;
@@ -276,6 +290,8 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
     }
     mbar_init(s_full, 2);
     mbar_init(s_empty, 1);
+    unit_q[0] = (int)blockIdx.x < num_units ? (int)blockIdx.x : -1;
+    *unit_tail = 1;
     fence_barrier_init();
     for (int l = 0; l < kL; ++l) tma_prefetch_desc(&maps.m[l]);
   }
@@ -290,7 +306,9 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
     uint32_t it = 0, hc = 0;   // tile / K-half slot counters
     // lane -> (frame, axis, a) of the tap this lane evaluates for every tile
     const int pf = lane / 14, pax = (lane % 14) / 7, pa = lane % 7;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (uint32_t ui = 0;; ++ui) {
+      const int u = unit_at(ui);
+      if (u < 0) break;
       const int n = u / kL, l = u % kL;
       const int H = g.lay.h[l], W = g.lay.w[l];
       const float inv = 1.0f / (float)(1 << l);
@@ -356,7 +374,8 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_16(128, 128, /*fp16*/ true);
       uint32_t it = 0, ui = 0, hc = 0;
       const uint32_t s_base = smem_u32(smem + OFF_S);
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+      for (;; ++ui) {
+        if (unit_at(ui) < 0) break;
         mbar_wait_spin(s_full, ui & 1u);
         for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
           const int acc = it % NACC;
@@ -390,7 +409,19 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
     const int atom = lane >> 4, chunk = (lane & 15) >> 1, half = lane & 1;  // where this lane's 4 channels live
     uint8_t* s0 = smem + OFF_S;
     uint32_t ui = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++ui) {
+    for (;; ++ui) {
+      if (sb == 0 && ui > 0) {           // draw the next unit and publish it
+        int nu = 0;
+        if (lane == 0) {
+          nu = (int)gridDim.x + atomicAdd(g.unit_counter, 1);
+          if (nu >= num_units) nu = -1;
+          unit_q[ui & 7] = nu;
+          __threadfence_block();
+          *unit_tail = (int)ui + 1;
+        }
+      }
+      const int u = unit_at(ui);
+      if (u < 0) break;
       const int n = u / kL, l = u % kL;
       const bool valid = g.track_valid == nullptr || g.track_valid[n] != 0;
       float4 rows[25];
@@ -425,7 +456,9 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
     uint16_t* img = reinterpret_cast<uint16_t*>(smem + OFF_IMG + grp * IMG_GROUP);
     const float* prm_base = reinterpret_cast<const float*>(smem + OFF_PARAM);
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (uint32_t ui = 0;; ++ui) {
+      const int u = unit_at(ui);
+      if (u < 0) break;
       const int n = u / kL, l = u % kL;
       for (int tp = 0; tp < tiles_per_unit; ++tp, ++it) {
         if ((int)(it % NGROUP) != grp) continue;
@@ -471,6 +504,12 @@ cudaError_t launch_corr_patch_t(const __nv_bfloat16* pyr_half, int H4, int W4, c
   g.T = T;
   g.N = N;
   g.vol = reinterpret_cast<uint16_t*>(vol);
+  // every level of the pyramid workspace has room for two 16-bit planes (launch_split_pyramid); this kernel's single
+  // fp16 plane uses the first half, so the unit counter can live right behind level 0's plane
+  const size_t plane0 = (size_t)T * g.lay.h[0] * g.lay.w[0] * kD * 2;
+  g.unit_counter = reinterpret_cast<int*>(reinterpret_cast<uintptr_t>(pyr_half) + ((plane0 + 15) & ~(size_t)15));
+  cudaError_t e0 = cudaMemsetAsync(g.unit_counter, 0, sizeof(int), s);
+  if (e0 != cudaSuccess) return e0;
   Corr3Maps maps;
   for (int l = 0; l < kL; ++l) {
     const uint64_t W = (uint64_t)g.lay.w[l], H = (uint64_t)g.lay.h[l];
