@@ -219,8 +219,9 @@ def test_updateformer_stage(eng, impl):
     assert err < 2e-4 * max(scale, 1.0), (err, scale)
 
 
-# 0: product kernels (fused tcgen05 time attention, mma.sync kernels for the space patterns),
-# 1: exact-fp32 SIMT cross-check, 2: like 0 with the tcgen05 point<-virtual attention kernel (attention_p2v.cu)
+# 0: product kernels (fused tcgen05 time attention, tcgen05 + TMA point<-virtual attention for more than 64 points,
+#    mma.sync kernels for the other space patterns), 1: exact-fp32 SIMT cross-check,
+# 2: like 0 with the mma.sync kernel for point<-virtual too (the kernel attention_p2v.cu replaced)
 @pytest.mark.parametrize("attn", [0, 1, 2])
 @pytest.mark.parametrize("N,T", [(70, 6), (600, 20), (130, 40), (1030, 16), (129, 5), (3, 2)])
 def test_updateformer_attention_shapes(eng, attn, N, T):
