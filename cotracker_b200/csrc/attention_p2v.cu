@@ -5,7 +5,7 @@
 //   0. ONE 3-D TMA box each brings the 128 query rows (48 fp32, rows T*ld apart in the track-major token layout), the 64
 //      key rows and the 64 value rows of the head into shared memory; the loads of head h+1 are issued as soon as head
 //      h's staging has been consumed, so they overlap its MMAs and softmax
-//   1. conversion (thread <-> 16-byte chunk, conflict-free shared-memory reads): fp32 -> split bf16 hi|lo planes written
+//   1. conversion (a quarter warp per query row, conflict-free): fp32 -> split bf16 hi|lo planes written
 //      as 128B-swizzled K-major operand tiles (q pre-multiplied by 48^-1/2 log2 e; head dim 48 zero-padded to the
 //      64-element swizzle row); V_h is written TRANSPOSED ([48 dims x 64 keys], K = keys) as the B operand of the
 //      second product
@@ -97,24 +97,23 @@ attn_p2v_tc_kernel(const __grid_constant__ P2vMaps maps, AttnParams p, int tiles
     mbar_wait(bar_ld, ph);
     // ---- 1. staging -> split operand tiles
     {
+      // Q: 8 lanes per row, lane slot s < 6 converts the row's 16-byte chunk s (8 channels), slots 6 and 7 re-zero the
+      // head-dim padding chunks (P lived there): a quarter warp writes one row = 8 distinct swizzle positions
       const float4* sq = reinterpret_cast<const float4*>(smem + PV_OFF_SQ);
+      const int slot = r & 7;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {               // 128 rows x 12 chunks of 4 floats
-        const int e = j * PV_THREADS + r;
-        const int row = e / 12, c = e % 12;
-        const float4 a = sq[e];
-        uint32_t h0, l0, h1, l1;
-        split2(a.x * qscale, a.y * qscale, h0, l0);
-        split2(a.z * qscale, a.w * qscale, h1, l1);
-        const uint32_t off = swz(row, c >> 1) + (uint32_t)((c & 1) * 8);
-        *reinterpret_cast<uint2*>(smem + PV_OFF_Q + off) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(smem + PV_OFF_Q + PV_TILE_Q + off) = make_uint2(l0, l1);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {                // head-dim padding (chunks 6, 7 of every row, both planes): P lived here
-        const int e = j * PV_THREADS + r;          // 512 chunks = 128 rows x 2 planes x 2 chunks
-        const int row = e >> 2, c = 6 + (e & 1), pl = (e >> 1) & 1;
-        *reinterpret_cast<uint4*>(smem + PV_OFF_Q + pl * PV_TILE_Q + swz(row, c)) = make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < 8; ++j) {
+        const int row = j * 16 + (r >> 3);
+        uint4 qh = make_uint4(0, 0, 0, 0), ql = make_uint4(0, 0, 0, 0);
+        if (slot < 6) {
+          const float4 a = sq[row * 12 + 2 * slot], b = sq[row * 12 + 2 * slot + 1];
+          split2(a.x * qscale, a.y * qscale, qh.x, ql.x);
+          split2(a.z * qscale, a.w * qscale, qh.y, ql.y);
+          split2(b.x * qscale, b.y * qscale, qh.z, ql.z);
+          split2(b.z * qscale, b.w * qscale, qh.w, ql.w);
+        }
+        *reinterpret_cast<uint4*>(smem + PV_OFF_Q + swz(row, slot)) = qh;
+        *reinterpret_cast<uint4*>(smem + PV_OFF_Q + PV_TILE_Q + swz(row, slot)) = ql;
       }
       const float4* sk = reinterpret_cast<const float4*>(smem + PV_OFF_SK) + kv_key * 12;
       const float4* sv = reinterpret_cast<const float4*>(smem + PV_OFF_SV) + kv_key * 12;
