@@ -169,7 +169,8 @@ int ct3_profile_read(double ms[7], int launches[7], double* gemm_flops);
  * lo plane cols [2432,4864); value = hi+lo, cols 2401..2431 are zero. */
 /* scratch: ct3_pyramid_layout's total * 4 bytes (256-byte aligned) for the split-bf16 pyramid copy of the
  * correlate-then-interpolate kernel (used when every level is >= 8x8 texels); NULL selects the
- * sample-then-correlate kernel. */
+ * sample-then-correlate kernel.  With prec.corr < 3 the copy is ONE fp16 plane per level (the first half of each
+ * level's region); the default kernel keeps its 4-byte work counter behind level 0's plane, zeroed by the call. */
 int ct3_corr_sample(const float* pyr, int H4, int W4, const float* support,
                     const uint8_t* track_valid, const float* coords, int T, int N,
                     void* vol_split, void* scratch, size_t scratch_bytes, ct3_stream_t stream);
