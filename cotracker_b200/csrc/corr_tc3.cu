@@ -239,7 +239,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, int acc, int q
   if (k == 0) {
 #pragma unroll
     for (int t2 = 0; t2 < 2; ++t2)
-      if (t2 < nf) bulk_store_s2g(vrow + (int64_t)t2 * kL * (ROW_BYTES / 2), reinterpret_cast<uint8_t*>(img) + t2 * ROW_BYTES, ROW_BYTES);
+      if (t2 < nf)
+        bulk_store_s2g_hint(vrow + (int64_t)t2 * kL * (ROW_BYTES / 2), reinterpret_cast<uint8_t*>(img) + t2 * ROW_BYTES, ROW_BYTES,
+                            l2_policy_evict_first());
     bulk_commit();
   }
 }
@@ -304,6 +306,9 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
   if (warp == TMA_WARP) {
     // ================================================================== TMA issuer + tap tables (whole warp)
     uint32_t it = 0, hc = 0;   // tile / K-half slot counters
+    // the 67 MB pyramid is read ~100x (6.7 GB of texel boxes per launch) while 3.9 GB of volume rows stream out: keep
+    // the texels in L2 (evict_last) and let the volume rows go first (evict_first in the epilogue's bulk copies)
+    const uint64_t keep = l2_policy_evict_last();
     // lane -> (frame, axis, a) of the tap this lane evaluates for every tile
     const int pf = lane / 14, pax = (lane % 14) / 7, pa = lane % 7;
     for (uint32_t ui = 0;; ++ui) {
@@ -359,8 +364,8 @@ corr_patch_t_kernel(const __grid_constant__ Corr3Args g, const __grid_constant__
               if (kh == 1) mbar_wait_spin(&a_empty[sl], ((h / NSLOT) & 1u) ^ 1u);
               mbar_arrive_expect_tx(&a_full[sl], (uint32_t)(nf * (A_SLOT / 2)));
               uint8_t* dst = smem + OFF_A + sl * A_SLOT;
-              tma_load_4d(dst, &maps.m[l], kh * 64, bx0, by0, t0 + k, &a_full[sl]);
-              if (nf == 2) tma_load_4d(dst + 8192, &maps.m[l], kh * 64, bx1, by1, t0 + k + 1, &a_full[sl]);
+              tma_load_4d_hint(dst, &maps.m[l], kh * 64, bx0, by0, t0 + k, &a_full[sl], keep);
+              if (nf == 2) tma_load_4d_hint(dst + 8192, &maps.m[l], kh * 64, bx1, by1, t0 + k + 1, &a_full[sl], keep);
             }
           }
           hc += 2;        // every lane tracks the slot counter (the table gate above is a warp-wide wait)
