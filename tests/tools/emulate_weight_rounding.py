@@ -4,7 +4,7 @@ A 2-product GEMM on fp16 planes keeps the activation exact to ~2^-22 (hi + lo) a
 (2^-12).  That is exactly the unmodified reference run with its transformer weights rounded to fp16, so the error of
 the scheme can be measured without writing the kernel.  Prints max |d tracks| against the committed golden of the case.
 
-    python scripts/emulate_weight_rounding.py c2_grid30 c2_grid30_stress c4_online_grid50
+    python tests/tools/emulate_weight_rounding.py c2_grid30 c2_grid30_stress c4_online_grid50
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import make_golden as mg  # noqa: E402

@@ -4,7 +4,7 @@ For every (prec.corr, prec.fc1) setting: max |d pred_tracks| (pixels) and visibi
 reference-generated fixtures at BASELINE scale -- unit-gain and amplified-head ("stress", ~20 px of motion) -- plus
 the headline step time.  The table goes to profiles/ and picks the library default (csrc/api.cu kDefPrec*).
 
-    python scripts/precision_sweep.py > gpurun_out/precision_sweep.txt
+    python tests/tools/precision_sweep.py > gpurun_out/precision_sweep.txt
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

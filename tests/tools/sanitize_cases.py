@@ -1,13 +1,13 @@
 """A small, fast pass over every hand-written kernel for compute-sanitizer (memcheck / synccheck / racecheck are
 10-100x slower than native, so the shapes are tiny).  Each case also checks its result against the CPU oracle.
-    compute-sanitizer --tool memcheck  python scripts/sanitize_cases.py > profiles/r2_sanitizer_memcheck.log
-    compute-sanitizer --tool synccheck python scripts/sanitize_cases.py > profiles/r2_sanitizer_synccheck.log"""
+    compute-sanitizer --tool memcheck  python tests/tools/sanitize_cases.py > profiles/r2_sanitizer_memcheck.log
+    compute-sanitizer --tool synccheck python tests/tools/sanitize_cases.py > profiles/r2_sanitizer_synccheck.log"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
