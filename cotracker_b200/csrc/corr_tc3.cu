@@ -12,7 +12,7 @@
 // texels the N side, so a thread of the epilogue owns ONE support vector k and sees all 64 raw correlations of a
 // frame as TMEM columns.  Both blends (x, then y) become plain FMAs on the thread's own registers with warp-uniform
 // weights: no shuffles, no exchange of texel rows between lanes -- corr_tc2.cu's epilogue (98 + 52 shuffles and a
-// shared-memory y-blend per tile) was what bounded that kernel (profiles/r2_corr_analysis.txt).
+// shared-memory y-blend per tile) was what bounded that kernel (profiles/r2_corr_tc3_history.txt).
 //
 //   pyramid  : ONE fp16 plane per level [T][H][W][128] (made once per update-loop call); texels are rounded to fp16
 //              (2^-12 relative), the support vectors are exact to a split fp16 pair (prec.corr = 2)
@@ -38,8 +38,14 @@
 //              otherwise idle lanes of the TMA warp.  The blend code exists ONCE (frame loop not unrolled): a fully
 //              unrolled epilogue is 290 KB of SASS and ran 5x slower on instruction-cache misses
 //              (profiles/r2_corr_tc3_history.txt).
+//   schedule : persistent CTAs; a unit = (track n, level l) = T frames of one support operand.  A CTA's first unit is
+//              blockIdx.x, the others come from a global counter (SMs differ by up to 10 % in speed on this kernel).
+//   L2       : texel boxes are loaded evict_last, volume rows stored evict_first (the 3.9 GB write stream would
+//              otherwise push the 67 MB pyramid, read ~100x, out of L2)
+// What was measured and NOT adopted (support rows duplicated into TMEM lanes 64..112 for a four-partition epilogue, the
+// A operand in tensor memory, rolling / two-phase packed-FMA epilogues): profiles/r2_corr_tc3_history.txt.
 // Warps (14): 0,1 / 4,5 / 8,9 / 12,13 epilogue groups (warp % 4 = TMEM lane quarter), 2 TMA issuer (+ tap tables),
-// 3 MMA issuer (+ TMEM alloc), 6,7 support builders, 10,11 idle.
+// 3 MMA issuer (+ TMEM alloc), 6,7 support builders (6 also draws the units), 10,11 idle.
 #include "gemm.cuh"
 #include "kernels.cuh"
 
